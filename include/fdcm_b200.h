@@ -1,0 +1,189 @@
+/* fdcm_b200.h — C ABI of the B200-native OpenFDCM hot paths (libfdcm_b200.so).
+ *
+ * Drop-in boundary for the two data-parallel hot paths of Innoptech/OpenFDCM v0.10.0:
+ *   (1) the DT3 feature-map build      (reference: buildCpuFeaturemap, matching/featuremaps/dt3cpu.h:174-234)
+ *   (2) template search / optimise / match (reference: search<DefaultMatch>, matching/src/matchstrategies/defaultmatch.cpp:32-89)
+ * Everything behind this header is hand-written sm_100a CUDA; there is NO CPU fallback: every
+ * compute entry point returns FDCM_ERR_CUDA when no device is usable.
+ *
+ * Conventions
+ *   - line arrays are packed float32 records [x1,y1,x2,y2] (the column-major memory image of the
+ *     reference's `LineArray = Eigen::Matrix<float,4,-1>`, core/math.h:66);
+ *   - 2x3 transforms are row-major [r00 r01 tx r10 r11 ty] (values of core::Mat23, math.h:64);
+ *   - plain pointers + sizes, caller owns every host buffer, the library owns opaque handles;
+ *   - every function returns an fdcm_status; fdcm_last_error() gives the message (thread-local);
+ *   - nothing throws across this boundary; empty inputs are not errors (empty scene -> empty map,
+ *     like dt3cpu.h:180-181; no templates -> no matches, like defaultmatch.cpp:40-41).
+ *
+ * `path:line` citations are relative to the reference tree.
+ */
+#ifndef FDCM_B200_H
+#define FDCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDCM_B200_ABI_VERSION 1
+
+typedef enum fdcm_status {
+    FDCM_OK = 0,
+    FDCM_ERR_INVALID = 1,      /* bad argument */
+    FDCM_ERR_CUDA = 2,         /* CUDA runtime failure / no device */
+    FDCM_ERR_NOMEM = 3,        /* host or device allocation failed */
+    FDCM_ERR_OUT_OF_RANGE = 4, /* penalize: tmpl_idx outside templatelengths (exponentialpenalty.cpp:47-62) */
+    FDCM_ERR_CAPACITY = 5      /* output buffer too small; *n_out holds the required count */
+} fdcm_status;
+
+/* core::Distance (core/imgproc.h:148) — same numeric values */
+typedef enum fdcm_distance { FDCM_L2 = 0, FDCM_L2_SQUARED = 1, FDCM_L1 = 2 } fdcm_distance;
+
+/* Dt3CpuParameters (dt3cpu.h:34-42) + the runtime distance of PyDt3CpuParameters (python/src/matching.cpp:51-60) */
+typedef struct fdcm_dt3_params {
+    int32_t depth;      /* number of orientation planes, 1..64 (reference default 30) */
+    float dt3_coeff;    /* orientation propagation coefficient (default 5) */
+    float padding;      /* padding ratio (default 2.2) */
+    int32_t distance;   /* fdcm_distance */
+} fdcm_dt3_params;
+
+/* matching::Match (matchstrategy.h:35-44): 32-byte POD */
+typedef struct fdcm_match {
+    int32_t tmpl_idx;
+    float score;
+    float transform[6];
+} fdcm_match;
+
+typedef enum fdcm_penalty_kind { FDCM_PENALTY_NONE = 0, FDCM_PENALTY_DEFAULT = 1, FDCM_PENALTY_EXPONENTIAL = 2 } fdcm_penalty_kind;
+
+/* DefaultSearch(max_tmpl_lines, max_scene_lines) (searchstrategies/defaultsearch.h:53-66),
+ * BatchOptimize(batch_size) (optimizestrategies/batchoptimize.h:8-23; batch_size == 0 selects the
+ * step-1 DefaultOptimize rules, defaultoptimize.cpp:49-64), optional fused penalty
+ * (penaltystrategies/{default,exponential}penalty.cpp) and top-K (sortMatches(matches, n), matchstrategy.h:52-55). */
+typedef struct fdcm_search_params {
+    int32_t max_tmpl_lines;
+    int32_t max_scene_lines;
+    int32_t batch_size;
+    int32_t penalty_kind;   /* fdcm_penalty_kind */
+    float penalty_tau;
+    int32_t top_k;          /* 0 = every match in hypothesis order (the reference's search() result);
+                               >0 = the top_k best (ascending score, ties by hypothesis order) */
+    int32_t tmpl_idx_base;  /* added to tmpl_idx in the emitted matches (template sharding keeps global indices) */
+} fdcm_search_params;
+
+typedef struct fdcm_dt3_info {
+    int32_t depth;
+    int32_t width, height;          /* feature size (dt3cpu.h:57 getFeatureSize) */
+    int32_t pitch;                  /* row pitch of the device planes, in floats */
+    float scene_translation[2];     /* dt3cpu.h:56 getSceneTranslation */
+    int32_t distance;
+    int32_t device;
+    int32_t n_scene_lines;
+    int32_t exact_dt_path;          /* 1: integer-exact fast DT path (side <= 2897), 0: literal general path */
+} fdcm_dt3_info;
+
+/* counters of the last search on a feature map */
+typedef struct fdcm_search_stats {
+    int64_t n_hypotheses;
+    int64_t n_valid;        /* hypotheses with a value (not nullopt) */
+    int64_t n_evaluations;  /* candidate translations scored */
+    int64_t n_lookups;      /* feature-map gathers = 2 * lines * evaluations */
+} fdcm_search_stats;
+
+typedef struct fdcm_dt3 fdcm_dt3;               /* device feature map: [depth][height][pitch] fp32 planes */
+typedef struct fdcm_templates fdcm_templates;   /* device-resident template set */
+
+const char* fdcm_last_error(void);
+int32_t fdcm_abi_version(void);
+fdcm_status fdcm_device_count(int32_t* n);
+/* Run every kernel of this library on a caller-owned CUDA stream (e.g. torch's current stream) of `device`;
+ * NULL restores the library's own stream. */
+fdcm_status fdcm_set_stream(int32_t device, void* cuda_stream);
+
+/* ---- hot path 1: feature map -------------------------------------------------------------- */
+/* buildCpuFeaturemap<D>(scene, params, pool) (dt3cpu.h:174-234). Blocking. `stage`: 0 = full map,
+ * 1 = stop after the distance transforms, 2 = stop after propagateOrientation (parity tests only). */
+fdcm_status fdcm_dt3_build(const float* scene_xyxy, int32_t n_lines, const fdcm_dt3_params* params, int32_t device,
+                           int32_t stage, fdcm_dt3** out);
+/* Same map object, new scene: reuses the device allocations when the new map fits. */
+fdcm_status fdcm_dt3_rebuild(fdcm_dt3* map, const float* scene_xyxy, int32_t n_lines);
+/* Re-run the build kernels on the scene lines already resident on the device (kernel-only timing). */
+fdcm_status fdcm_dt3_rerun(fdcm_dt3* map);
+fdcm_status fdcm_dt3_retain(fdcm_dt3* map);
+fdcm_status fdcm_dt3_release(fdcm_dt3* map);
+fdcm_status fdcm_dt3_get_info(const fdcm_dt3* map, fdcm_dt3_info* info);
+/* the `depth` angle keys in plane order (dt3cpu.h:188-190) */
+fdcm_status fdcm_dt3_angles(const fdcm_dt3* map, float* keys);
+/* Dt3Cpu::getDt3Map()[angle_i] as a dense row-major height x width image (python: get_dt3_map) */
+fdcm_status fdcm_dt3_download_plane(const fdcm_dt3* map, int32_t plane, float* dst);
+/* rasterised edge mask of plane i (1 = edge pixel), height x width bytes (drawLines, core/drawing.h:111-125) */
+fdcm_status fdcm_dt3_download_mask(const fdcm_dt3* map, int32_t plane, uint8_t* dst);
+/* orientation plane of each scene line (classifyLines, dt3cpu.h:123-134) */
+fdcm_status fdcm_dt3_scene_bins(const fdcm_dt3* map, int32_t* bins);
+/* raw device pointer of the planes (for zero-copy consumers, e.g. torch.from_blob / NCCL broadcast) */
+fdcm_status fdcm_dt3_device_ptr(const fdcm_dt3* map, void** planes, uint64_t* n_bytes);
+
+/* minmaxTranslation<Dt3Cpu>(featuremap, tmpl, align_vec) (dt3cpu.cpp:119-124, :30-75) */
+fdcm_status fdcm_dt3_minmax_translation(const fdcm_dt3* map, const float* tmpl_xyxy, int32_t n_lines,
+                                        const float align_vec[2], float out_min_max[2]);
+/* evaluate<Dt3Cpu>(featuremap, templates, translations) (dt3cpu.cpp:126-179).
+ * templates: CSR (tmpl_lines, tmpl_offsets[n_tmpl+1]); translations: CSR of (x,y) pairs
+ * (translations, transl_offsets[n_tmpl+1]); scores: transl_offsets[n_tmpl] floats. */
+fdcm_status fdcm_dt3_evaluate(const fdcm_dt3* map, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                              const float* translations, const int32_t* transl_offsets, float* scores);
+/* closestOrientation (dt3cpu.h:93-114) of arbitrary lines against this map's planes, computed on the
+ * device through the slope-threshold table (parity hook for the bin assignment of template lines) */
+fdcm_status fdcm_dt3_classify(const fdcm_dt3* map, const float* lines_xyxy, int32_t n_lines, int32_t* bins);
+
+/* ---- hot path 2: search ------------------------------------------------------------------- */
+/* Upload a template set once (templates are typically static across scenes). */
+fdcm_status fdcm_templates_create(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, int32_t device,
+                                  fdcm_templates** out);
+fdcm_status fdcm_templates_release(fdcm_templates* t);
+/* getTemplateLengths (core/math.h:319-324) */
+fdcm_status fdcm_templates_lengths(const fdcm_templates* t, float* lengths);
+
+/* search(DefaultMatch, DefaultSearch, BatchOptimize|DefaultOptimize, featuremap, templates, scene)
+ * (defaultmatch.cpp:32-89) [+ penalize + sort/top-k]. `scene_xyxy` is the ORIGINAL scene
+ * (un-shifted), as in the reference. out: capacity records; *n_out = number written (or required
+ * when FDCM_ERR_CAPACITY). */
+fdcm_status fdcm_search(const fdcm_dt3* map, const fdcm_templates* templates, const float* scene_xyxy, int32_t n_scene,
+                        const fdcm_search_params* params, fdcm_match* out, int64_t capacity, int64_t* n_out);
+/* one-shot variant taking host templates (uploads, searches, frees) */
+fdcm_status fdcm_search_host(const fdcm_dt3* map, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                             const float* scene_xyxy, int32_t n_scene, const fdcm_search_params* params,
+                             fdcm_match* out, int64_t capacity, int64_t* n_out);
+/* the hypothesis list of the last fdcm_search on this map: 4 ints per hypothesis
+ * (tmpl_idx, tmpl_line_idx, scene_line_idx, reversed) in hypothesis order (parity hook) */
+fdcm_status fdcm_search_last_hypotheses(const fdcm_dt3* map, int32_t* out, int64_t capacity, int64_t* n_out);
+fdcm_status fdcm_search_last_stats(const fdcm_dt3* map, fdcm_search_stats* stats);
+
+/* establishSearchStrategy<DefaultSearch> for one template (defaultsearch.cpp:29-49): pairs of
+ * (tmpl_line_idx, scene_line_idx); host-side helper mirroring the SearchStrategy concept. */
+fdcm_status fdcm_default_search(const float* tmpl_xyxy, int32_t n_tmpl_lines, const float* scene_xyxy, int32_t n_scene,
+                                int32_t max_tmpl_lines, int32_t max_scene_lines, int32_t* out_pairs, int32_t capacity,
+                                int32_t* n_out);
+
+/* penalize (penaltystrategies/{default,exponential}penalty.cpp) and sort_matches
+ * (python/src/matching.cpp:302-307) on host match lists — O(#matches) host helpers */
+fdcm_status fdcm_penalize(int32_t penalty_kind, float tau, fdcm_match* matches, int64_t n, const float* lengths,
+                          int64_t n_lengths);
+fdcm_status fdcm_sort_matches(fdcm_match* matches, int64_t n);
+/* getTemplateLengths without a device */
+fdcm_status fdcm_template_lengths(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, float* lengths);
+
+/* ---- per-kernel timing (CUDA events on the launching stream; feeds bench.py's roofline) ------ */
+fdcm_status fdcm_profile_enable(int32_t on);
+fdcm_status fdcm_profile_reset(void);
+/* n-th recorded kernel: name, total ms, launches, algorithmic bytes per launch (last launch) */
+fdcm_status fdcm_profile_get(int32_t index, char* name, int32_t name_cap, double* total_ms, int64_t* launches,
+                             double* bytes_per_launch);
+fdcm_status fdcm_profile_count(int32_t* n);
+/* number of kernels this library launched since process start */
+int64_t fdcm_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDCM_B200_H */

@@ -1,0 +1,933 @@
+// fdcm_api.cu — C ABI of libfdcm_b200 (declared in include/fdcm_b200.h): handle management, the
+// O(#lines) host preparation the reference also does on the host (scene shift, orientation bins via
+// the host libm, std::sort orderings), stream / workspace plumbing and per-kernel CUDA-event timing.
+// There is deliberately no CPU compute path here: if CUDA is unavailable every entry point fails.
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "host_math.hpp"
+#include "kernels.h"
+
+using namespace fdcm;
+
+// =============================================================================================
+// error handling
+// =============================================================================================
+static thread_local std::string g_last_error;
+
+static fdcm_status fail(fdcm_status st, const std::string& msg) {
+    g_last_error = msg;
+    return st;
+}
+
+#define CUDA_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        cudaError_t _e = (expr);                                                                           \
+        if (_e != cudaSuccess)                                                                             \
+            return fail(_e == cudaErrorMemoryAllocation ? FDCM_ERR_NOMEM : FDCM_ERR_CUDA,                  \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));                              \
+    } while (0)
+
+extern "C" const char* fdcm_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t fdcm_abi_version(void) { return FDCM_B200_ABI_VERSION; }
+
+extern "C" fdcm_status fdcm_device_count(int32_t* n) {
+    if (!n) return fail(FDCM_ERR_INVALID, "n is null");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return fail(FDCM_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    }
+    *n = c;
+    return FDCM_OK;
+}
+
+// =============================================================================================
+// streams, launch counter, per-kernel event timing
+// =============================================================================================
+static std::mutex g_mutex;
+static std::map<int, cudaStream_t> g_own_streams, g_user_streams;
+static std::atomic<long long> g_launches{0};
+
+static fdcm_status get_stream(int device, cudaStream_t* s) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto u = g_user_streams.find(device);
+    if (u != g_user_streams.end()) { *s = u->second; return FDCM_OK; }
+    auto o = g_own_streams.find(device);
+    if (o == g_own_streams.end()) {
+        cudaStream_t ns;
+        CUDA_TRY(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+        o = g_own_streams.emplace(device, ns).first;
+    }
+    *s = o->second;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_set_stream(int32_t device, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (cuda_stream) g_user_streams[device] = (cudaStream_t)cuda_stream;
+    else g_user_streams.erase(device);
+    return FDCM_OK;
+}
+
+struct ProfEntry { double total_ms = 0; long long launches = 0; double bytes = 0; };
+struct ProfPending { std::string name; cudaEvent_t a, b; double bytes; };
+static bool g_prof_on = false;
+static std::vector<std::string> g_prof_order;
+static std::map<std::string, ProfEntry> g_prof;
+static std::vector<ProfPending> g_prof_pending;
+
+struct KernelScope {   // brackets one kernel launch
+    cudaStream_t s;
+    bool on;
+    ProfPending p;
+    KernelScope(const char* name, double bytes, cudaStream_t stream, int n_kernels = 1) : s(stream), on(g_prof_on) {
+        g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
+        if (on) {
+            p.name = name;
+            p.bytes = bytes;
+            cudaEventCreate(&p.a);
+            cudaEventCreate(&p.b);
+            cudaEventRecord(p.a, s);
+        }
+    }
+    ~KernelScope() {
+        if (on) {
+            cudaEventRecord(p.b, s);
+            std::lock_guard<std::mutex> lk(g_mutex);
+            g_prof_pending.push_back(p);
+        }
+    }
+};
+
+static void prof_resolve() {   // call after the stream has been synchronised
+    std::lock_guard<std::mutex> lk(g_mutex);
+    for (auto& p : g_prof_pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (!g_prof.count(p.name)) g_prof_order.push_back(p.name);
+            auto& e = g_prof[p.name];
+            e.total_ms += ms;
+            e.launches += 1;
+            e.bytes = p.bytes;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_pending.clear();
+}
+
+extern "C" fdcm_status fdcm_profile_enable(int32_t on) { g_prof_on = on != 0; return FDCM_OK; }
+extern "C" fdcm_status fdcm_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    g_prof.clear();
+    g_prof_order.clear();
+    return FDCM_OK;
+}
+extern "C" fdcm_status fdcm_profile_count(int32_t* n) {
+    if (!n) return fail(FDCM_ERR_INVALID, "n is null");
+    std::lock_guard<std::mutex> lk(g_mutex);
+    *n = (int32_t)g_prof_order.size();
+    return FDCM_OK;
+}
+extern "C" fdcm_status fdcm_profile_get(int32_t index, char* name, int32_t name_cap, double* total_ms, int64_t* launches,
+                                        double* bytes_per_launch) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    if (index < 0 || index >= (int32_t)g_prof_order.size()) return fail(FDCM_ERR_INVALID, "profile index out of range");
+    const std::string& nm = g_prof_order[index];
+    const ProfEntry& e = g_prof[nm];
+    if (name && name_cap > 0) {
+        std::strncpy(name, nm.c_str(), name_cap - 1);
+        name[name_cap - 1] = 0;
+    }
+    if (total_ms) *total_ms = e.total_ms;
+    if (launches) *launches = e.launches;
+    if (bytes_per_launch) *bytes_per_launch = e.bytes;
+    return FDCM_OK;
+}
+extern "C" int64_t fdcm_kernel_launch_count(void) { return g_launches.load(); }
+
+// =============================================================================================
+// device buffer with grow-only capacity
+// =============================================================================================
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// =============================================================================================
+// feature map handle
+// =============================================================================================
+struct fdcm_dt3 {
+    std::atomic<int> refs{1};
+    fdcm_dt3_params params{};
+    int device = 0;
+    int stage = 0;
+    MapDims dm{};
+    float shift[2] = {0.f, 0.f};
+    bool exact = true;
+    int n_lines = 0;
+    std::vector<float> keys;
+    std::vector<int32_t> scene_bins;
+    SlopeTable table;
+    SlopeTableDev table_dev{};
+    PropParams prop{};
+    IntegralParams integ{};
+    DevBuf planes, mask, g, stack, lines, bins;
+    // search workspace (mutable state of the last search on this map)
+    mutable std::mutex search_mutex;
+    mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
+        s_topk_out, s_topk_n;
+    mutable int64_t last_n_hyp = 0;
+    mutable fdcm_search_stats last_stats{};
+    mutable void* h_pinned = nullptr;   // pinned staging for match download
+    mutable size_t h_pinned_cap = 0;
+
+    ~fdcm_dt3() {
+        cudaSetDevice(device);
+        for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
+                          &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n})
+            b->release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+    }
+};
+
+static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s);
+
+// host preparation: shift, size, keys, bins (reference dt3cpu.h:180-193), then upload
+static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n_lines, cudaStream_t s) {
+    m->n_lines = n_lines;
+    m->scene_bins.clear();
+    if (n_lines == 0) {   // dt3cpu.h:180-181: empty map, translation (0,0), size (0,0)
+        m->dm = MapDims{0, 0, 0, 0, 0, 0};
+        m->shift[0] = m->shift[1] = 0.f;
+        m->keys.clear();
+        return FDCM_OK;
+    }
+    int64_t size[2];
+    scene_centered_translation(scene, n_lines, m->params.padding, m->shift, size);
+    if (size[0] <= 0 || size[0] > 65534 || size[1] != size[0])
+        return fail(FDCM_ERR_INVALID, "feature size out of the supported range (1..65534): " + std::to_string(size[0]));
+    m->keys = angle_keys(m->params.depth);
+    const int D = (int)m->keys.size();
+    MapDims dm;
+    dm.D = D;
+    dm.W = (int)size[0];
+    dm.H = (int)size[1];
+    dm.pitch = (dm.W + 31) / 32 * 32;
+    dm.wwords = dm.pitch / 32;
+    dm.plane_elems = (size_t)dm.H * dm.pitch;
+    m->dm = dm;
+    // every intermediate of the reference's first/second L2 pass is an exact integer iff 2*(side-1)^2 < 2^24
+    m->exact = 2.0 * (double)(dm.W - 1) * (double)(dm.W - 1) < 16777216.0;
+
+    // translated scene (core/math.h:352-354) and orientation bins with the host libm (dt3cpu.h:123-134)
+    std::vector<float> ts((size_t)4 * n_lines);
+    m->scene_bins.resize(n_lines);
+    for (int64_t i = 0; i < 2 * (int64_t)n_lines; ++i) {
+        ts[2 * i] = scene[2 * i] + m->shift[0];
+        ts[2 * i + 1] = scene[2 * i + 1] + m->shift[1];
+    }
+    for (int i = 0; i < n_lines; ++i) m->scene_bins[i] = bin_of_line(m->keys.data(), D, &ts[4 * (size_t)i]);
+
+    // tables
+    m->table = build_slope_table(m->keys.data(), D);
+    if ((int)m->table.thr.size() > kMaxDepthDev + 8) return fail(FDCM_ERR_INVALID, "slope table too large");
+    m->table_dev.n_thr = (int)m->table.thr.size();
+    m->table_dev.nan_bin = m->table.nan_bin;
+    for (size_t i = 0; i < m->table.thr.size(); ++i) m->table_dev.thr[i] = m->table.thr[i];
+    for (size_t i = 0; i < m->table.piece_bin.size(); ++i) m->table_dev.piece_bin[i] = (uint8_t)m->table.piece_bin[i];
+    const std::vector<PropStep> steps = propagation_schedule(m->keys, m->params.dt3_coeff);
+    m->prop.n_steps = (int)steps.size();
+    for (size_t i = 0; i < steps.size(); ++i) {
+        m->prop.w[i] = steps[i].w;
+        m->prop.c1[i] = (uint8_t)steps[i].c1;
+        m->prop.c2[i] = (uint8_t)steps[i].c2;
+    }
+    for (int d = 0; d < D; ++d) {
+        const IntegralDir id = integral_direction(m->keys[d]);
+        m->integ.rx[d] = id.rx;
+        m->integ.ry[d] = id.ry;
+        m->integ.mode[d] = id.mode;
+    }
+
+    // device allocations (grow-only)
+    const size_t n_px = (size_t)D * dm.plane_elems;
+    CUDA_TRY(m->planes.reserve(n_px * sizeof(float)));
+    CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t)));
+    if (m->exact) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
+    if (m->params.distance != FDCM_L1) CUDA_TRY(m->stack.reserve(n_px * 8));
+    CUDA_TRY(m->lines.reserve((size_t)n_lines * 16));
+    CUDA_TRY(m->bins.reserve((size_t)n_lines * 4));
+    CUDA_TRY(cudaMemcpyAsync(m->lines.p, ts.data(), (size_t)n_lines * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->bins.p, m->scene_bins.data(), (size_t)n_lines * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // ts / scene_bins are pageable temporaries
+    return FDCM_OK;
+}
+
+static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
+    if (m->n_lines == 0) return FDCM_OK;
+    const MapDims& dm = m->dm;
+    const double N = (double)dm.D * dm.H * dm.W * 4.0;   // algorithmic plane bytes
+    const size_t mask_bytes = (size_t)dm.D * dm.H * dm.wwords * sizeof(uint32_t);
+    {
+        KernelScope k("mask_clear", (double)mask_bytes, s, 0);   // cudaMemsetAsync, not one of our kernels
+        CUDA_TRY(cudaMemsetAsync(m->mask.p, 0, mask_bytes, s));
+    }
+    {
+        KernelScope k("raster", 0.0, s);
+        launch_raster(m->lines.as<float>(), m->bins.as<int32_t>(), m->n_lines, dm, m->mask.as<uint32_t>(), s);
+    }
+    const int dist = m->params.distance;
+    if (m->exact) {
+        {
+            KernelScope k("dt_col_exact", N / 2, s);
+            launch_dt_col_exact(m->mask.as<uint32_t>(), dm, m->g.as<uint16_t>(), s);
+        }
+        if (dist == FDCM_L1) {
+            KernelScope k("dt_row_l1", N / 2 + N, s);
+            launch_dt_row_l1(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
+        } else {
+            KernelScope k("dt_row_literal", N / 2 + N, s);
+            launch_dt_pass_literal(true, true, m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->stack.p, s);
+        }
+    } else {
+        {
+            KernelScope k("mask_to_float", N, s);
+            launch_mask_to_float(m->mask.as<uint32_t>(), dm, m->planes.as<float>(), s);
+        }
+        if (dist == FDCM_L1) {
+            // L1 stays integer-exact at any size: build the u16 vertical distance on the fly
+            CUDA_TRY(m->g.reserve((size_t)dm.D * dm.plane_elems * sizeof(uint16_t)));
+            {
+                KernelScope k("dt_col_exact", N / 2, s);
+                launch_dt_col_exact(m->mask.as<uint32_t>(), dm, m->g.as<uint16_t>(), s);
+            }
+            KernelScope k("dt_row_l1", N / 2 + N, s);
+            launch_dt_row_l1(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
+        } else {
+            {
+                KernelScope k("dt_col_literal", 2 * N, s);
+                launch_dt_pass_literal(false, false, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
+            }
+            KernelScope k("dt_row_literal", 2 * N, s);
+            launch_dt_pass_literal(false, true, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
+        }
+    }
+    const bool need_sqrt = dist == FDCM_L2;
+    if (m->stage == 1) {
+        if (need_sqrt) {
+            KernelScope k("sqrt", 2 * N, s);
+            launch_sqrt(m->planes.as<float>(), dm, s);
+        }
+    } else {
+        {
+            KernelScope k("propagate", 2 * N, s);
+            launch_propagate(m->planes.as<float>(), dm, m->prop, need_sqrt, s);
+        }
+        if (m->stage == 0) {
+            KernelScope k("integral", 2 * N, s);
+            launch_integral(m->planes.as<float>(), dm, m->integ, s);
+        }
+    }
+    CUDA_TRY(cudaGetLastError());
+    return FDCM_OK;
+}
+
+static fdcm_status validate_params(const fdcm_dt3_params* p) {
+    if (!p) return fail(FDCM_ERR_INVALID, "params is null");
+    if (p->depth < 1 || p->depth > kMaxDepth) return fail(FDCM_ERR_INVALID, "depth must be in 1..64");
+    if (p->distance < 0 || p->distance > 2) return fail(FDCM_ERR_INVALID, "unknown distance");
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_build(const float* scene_xyxy, int32_t n_lines, const fdcm_dt3_params* params, int32_t device,
+                                      int32_t stage, fdcm_dt3** out) {
+    if (!out) return fail(FDCM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (fdcm_status st = validate_params(params)) return st;
+    if (n_lines < 0 || (n_lines > 0 && !scene_xyxy)) return fail(FDCM_ERR_INVALID, "bad scene");
+    if (stage < 0 || stage > 2) return fail(FDCM_ERR_INVALID, "bad stage");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(device, &s)) return st;
+    fdcm_dt3* m = new (std::nothrow) fdcm_dt3();
+    if (!m) return fail(FDCM_ERR_NOMEM, "host allocation failed");
+    m->params = *params;
+    m->device = device;
+    m->stage = stage;
+    fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
+    if (st == FDCM_OK) st = run_build_kernels(m, s);
+    if (st == FDCM_OK) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("build: ") + cudaGetErrorString(e));
+    }
+    prof_resolve();
+    if (st != FDCM_OK) {
+        delete m;
+        return st;
+    }
+    *out = m;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_rebuild(fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines) {
+    if (!m) return fail(FDCM_ERR_INVALID, "map is null");
+    if (n_lines < 0 || (n_lines > 0 && !scene_xyxy)) return fail(FDCM_ERR_INVALID, "bad scene");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
+    if (st == FDCM_OK) st = run_build_kernels(m, s);
+    if (st == FDCM_OK) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("rebuild: ") + cudaGetErrorString(e));
+    }
+    prof_resolve();
+    return st;
+}
+
+extern "C" fdcm_status fdcm_dt3_rerun(fdcm_dt3* m) {
+    if (!m) return fail(FDCM_ERR_INVALID, "map is null");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    fdcm_status st = run_build_kernels(m, s);
+    if (st == FDCM_OK) {
+        cudaError_t e = cudaStreamSynchronize(s);
+        if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("rerun: ") + cudaGetErrorString(e));
+    }
+    prof_resolve();
+    return st;
+}
+
+extern "C" fdcm_status fdcm_dt3_retain(fdcm_dt3* m) {
+    if (!m) return fail(FDCM_ERR_INVALID, "map is null");
+    m->refs.fetch_add(1);
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_release(fdcm_dt3* m) {
+    if (!m) return FDCM_OK;
+    if (m->refs.fetch_sub(1) == 1) delete m;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_get_info(const fdcm_dt3* m, fdcm_dt3_info* info) {
+    if (!m || !info) return fail(FDCM_ERR_INVALID, "null argument");
+    info->depth = m->dm.D;
+    info->width = m->dm.W;
+    info->height = m->dm.H;
+    info->pitch = m->dm.pitch;
+    info->scene_translation[0] = m->shift[0];
+    info->scene_translation[1] = m->shift[1];
+    info->distance = m->params.distance;
+    info->device = m->device;
+    info->n_scene_lines = m->n_lines;
+    info->exact_dt_path = m->exact ? 1 : 0;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_angles(const fdcm_dt3* m, float* keys) {
+    if (!m || !keys) return fail(FDCM_ERR_INVALID, "null argument");
+    std::memcpy(keys, m->keys.data(), m->keys.size() * sizeof(float));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_download_plane(const fdcm_dt3* m, int32_t plane, float* dst) {
+    if (!m || !dst) return fail(FDCM_ERR_INVALID, "null argument");
+    if (plane < 0 || plane >= m->dm.D) return fail(FDCM_ERR_INVALID, "plane out of range");
+    CUDA_TRY(cudaSetDevice(m->device));
+    const float* src = m->planes.as<float>() + (size_t)plane * m->dm.plane_elems;
+    CUDA_TRY(cudaMemcpy2D(dst, (size_t)m->dm.W * 4, src, (size_t)m->dm.pitch * 4, (size_t)m->dm.W * 4, m->dm.H,
+                          cudaMemcpyDeviceToHost));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_download_mask(const fdcm_dt3* m, int32_t plane, uint8_t* dst) {
+    if (!m || !dst) return fail(FDCM_ERR_INVALID, "null argument");
+    if (plane < 0 || plane >= m->dm.D) return fail(FDCM_ERR_INVALID, "plane out of range");
+    CUDA_TRY(cudaSetDevice(m->device));
+    std::vector<uint32_t> w((size_t)m->dm.H * m->dm.wwords);
+    CUDA_TRY(cudaMemcpy(w.data(), m->mask.as<uint32_t>() + (size_t)plane * m->dm.H * m->dm.wwords, w.size() * 4,
+                        cudaMemcpyDeviceToHost));
+    for (int y = 0; y < m->dm.H; ++y)
+        for (int x = 0; x < m->dm.W; ++x)
+            dst[(size_t)y * m->dm.W + x] = (w[(size_t)y * m->dm.wwords + (x >> 5)] >> (x & 31)) & 1u;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_scene_bins(const fdcm_dt3* m, int32_t* bins) {
+    if (!m || !bins) return fail(FDCM_ERR_INVALID, "null argument");
+    std::memcpy(bins, m->scene_bins.data(), m->scene_bins.size() * sizeof(int32_t));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_device_ptr(const fdcm_dt3* m, void** planes, uint64_t* n_bytes) {
+    if (!m || !planes) return fail(FDCM_ERR_INVALID, "null argument");
+    *planes = m->planes.p;
+    if (n_bytes) *n_bytes = (uint64_t)m->dm.D * m->dm.plane_elems * 4;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_minmax_translation(const fdcm_dt3* m, const float* tmpl, int32_t n_lines, const float align_vec[2],
+                                                   float out[2]) {
+    if (!m || !align_vec || !out || (n_lines > 0 && !tmpl)) return fail(FDCM_ERR_INVALID, "null argument");
+    const int64_t fs[2] = {m->dm.W, m->dm.H};
+    minmax_translation(tmpl, n_lines, align_vec, fs, m->shift, out);
+    return FDCM_OK;
+}
+
+static MapView map_view(const fdcm_dt3* m) {
+    MapView v;
+    v.planes = m->planes.as<float>();
+    v.dm = m->dm;
+    v.shift_x = m->shift[0];
+    v.shift_y = m->shift[1];
+    return v;
+}
+
+extern "C" fdcm_status fdcm_dt3_evaluate(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                                         const float* translations, const int32_t* transl_offsets, float* scores) {
+    if (!m || !tmpl_offsets || !transl_offsets) return fail(FDCM_ERR_INVALID, "null argument");
+    if (n_tmpl <= 0) return FDCM_OK;
+    const int64_t n_lines = tmpl_offsets[n_tmpl], n_scores = transl_offsets[n_tmpl];
+    if (n_scores <= 0) return FDCM_OK;
+    if (!scores || !translations || (n_lines > 0 && !tmpl_lines)) return fail(FDCM_ERR_INVALID, "null argument");
+    if (m->dm.D == 0) return fail(FDCM_ERR_INVALID, "evaluate on an empty feature map");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    std::vector<int32_t> owner((size_t)n_scores);
+    for (int t = 0; t < n_tmpl; ++t)
+        for (int i = transl_offsets[t]; i < transl_offsets[t + 1]; ++i) owner[i] = t;
+    DevBuf dl, doff, dtr, down, dsc;
+    auto cleanup = [&]() { for (DevBuf* b : {&dl, &doff, &dtr, &down, &dsc}) b->release(); };
+    cudaError_t e = cudaSuccess;
+    if (e == cudaSuccess) e = dl.reserve(std::max<size_t>(16, (size_t)n_lines * 16));
+    if (e == cudaSuccess) e = doff.reserve((size_t)(n_tmpl + 1) * 4);
+    if (e == cudaSuccess) e = dtr.reserve((size_t)n_scores * 8);
+    if (e == cudaSuccess) e = down.reserve((size_t)n_scores * 4);
+    if (e == cudaSuccess) e = dsc.reserve((size_t)n_scores * 4);
+    if (e == cudaSuccess && n_lines) e = cudaMemcpyAsync(dl.p, tmpl_lines, (size_t)n_lines * 16, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(doff.p, tmpl_offsets, (size_t)(n_tmpl + 1) * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dtr.p, translations, (size_t)n_scores * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(down.p, owner.data(), (size_t)n_scores * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        KernelScope k("evaluate", 0.0, s);
+        launch_evaluate(map_view(m), m->table_dev, dl.as<float4>(), doff.as<int32_t>(), dtr.as<float2>(), nullptr, down.as<int32_t>(),
+                        n_scores, dsc.as<float>(), s);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(scores, dsc.p, (size_t)n_scores * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    prof_resolve();
+    cleanup();
+    if (e != cudaSuccess) return fail(FDCM_ERR_CUDA, std::string("evaluate: ") + cudaGetErrorString(e));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_dt3_classify(const fdcm_dt3* m, const float* lines, int32_t n, int32_t* bins) {
+    if (!m || (n > 0 && (!lines || !bins))) return fail(FDCM_ERR_INVALID, "null argument");
+    if (n <= 0) return FDCM_OK;
+    if (m->dm.D == 0) return fail(FDCM_ERR_INVALID, "classify on an empty feature map");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    DevBuf dl, db;
+    cudaError_t e = dl.reserve((size_t)n * 16);
+    if (e == cudaSuccess) e = db.reserve((size_t)n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dl.p, lines, (size_t)n * 16, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        KernelScope k("classify", 0.0, s);
+        launch_classify(m->table_dev, dl.as<float4>(), n, db.as<int32_t>(), s);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(bins, db.p, (size_t)n * 4, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    prof_resolve();
+    dl.release();
+    db.release();
+    if (e != cudaSuccess) return fail(FDCM_ERR_CUDA, std::string("classify: ") + cudaGetErrorString(e));
+    return FDCM_OK;
+}
+
+// =============================================================================================
+// template sets
+// =============================================================================================
+struct fdcm_templates {
+    int device = 0;
+    int32_t n_tmpl = 0;
+    int32_t max_lines = 0;
+    int64_t n_lines = 0;
+    std::vector<int32_t> offsets;     // host copy
+    std::vector<float> lengths;       // getTemplateLengths
+    DevBuf lines, offs, argsort, line_len, denom;
+    int denom_kind = -1;
+    float denom_tau = 0.f;
+    std::mutex mu;
+    ~fdcm_templates() {
+        cudaSetDevice(device);
+        for (DevBuf* b : {&lines, &offs, &argsort, &line_len, &denom}) b->release();
+    }
+};
+
+static void template_host_prep(const float* tl, const int32_t* off, int32_t T, std::vector<float>& line_len,
+                               std::vector<int32_t>& argsort, std::vector<float>& lengths) {
+    const int64_t n = off[T];
+    line_len.resize((size_t)n);
+    argsort.resize((size_t)n);
+    lengths.resize((size_t)T);
+    auto work = [&](int t0, int t1) {
+        for (int t = t0; t < t1; ++t) {
+            const int l0 = off[t], L = off[t + 1] - off[t];
+            for (int i = 0; i < L; ++i) line_len[(size_t)l0 + i] = line_length(tl + 4 * ((size_t)l0 + i));
+            const std::vector<long> idx = argsort_desc(line_len.data() + l0, L);   // defaultsearch.cpp:35
+            for (int i = 0; i < L; ++i) argsort[(size_t)l0 + i] = (int32_t)idx[(size_t)i];
+            lengths[(size_t)t] = eigen_sum(line_len.data() + l0, L);              // math.h:319-324
+        }
+    };
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    const int nt = (T >= 512) ? std::min(hw, 16) : 1;
+    if (nt <= 1) { work(0, T); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < nt; ++i) th.emplace_back(work, (int)((int64_t)T * i / nt), (int)((int64_t)T * (i + 1) / nt));
+    for (auto& t : th) t.join();
+}
+
+extern "C" fdcm_status fdcm_templates_create(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, int32_t device,
+                                             fdcm_templates** out) {
+    if (!out) return fail(FDCM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (n_tmpl < 0 || !tmpl_offsets) return fail(FDCM_ERR_INVALID, "bad template offsets");
+    for (int t = 0; t < n_tmpl; ++t)
+        if (tmpl_offsets[t + 1] < tmpl_offsets[t]) return fail(FDCM_ERR_INVALID, "template offsets must be non-decreasing");
+    const int64_t n = tmpl_offsets[n_tmpl];
+    if (n > 0 && !tmpl_lines) return fail(FDCM_ERR_INVALID, "tmpl_lines is null");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(device, &s)) return st;
+    fdcm_templates* t = new (std::nothrow) fdcm_templates();
+    if (!t) return fail(FDCM_ERR_NOMEM, "host allocation failed");
+    t->device = device;
+    t->n_tmpl = n_tmpl;
+    t->n_lines = n;
+    t->offsets.assign(tmpl_offsets, tmpl_offsets + n_tmpl + 1);
+    for (int i = 0; i < n_tmpl; ++i) t->max_lines = std::max(t->max_lines, tmpl_offsets[i + 1] - tmpl_offsets[i]);
+    std::vector<float> line_len;
+    std::vector<int32_t> argsort;
+    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, line_len, argsort, t->lengths);
+    cudaError_t e = t->lines.reserve(std::max<size_t>(16, (size_t)n * 16));
+    if (e == cudaSuccess) e = t->offs.reserve((size_t)(n_tmpl + 1) * 4);
+    if (e == cudaSuccess) e = t->argsort.reserve(std::max<size_t>(4, (size_t)n * 4));
+    if (e == cudaSuccess) e = t->line_len.reserve(std::max<size_t>(4, (size_t)n * 4));
+    if (e == cudaSuccess) e = t->denom.reserve(std::max<size_t>(4, (size_t)n_tmpl * 4));
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->lines.p, tmpl_lines, (size_t)n * 16, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t->offs.p, tmpl_offsets, (size_t)(n_tmpl + 1) * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->argsort.p, argsort.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->line_len.p, line_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        delete t;
+        return fail(e == cudaErrorMemoryAllocation ? FDCM_ERR_NOMEM : FDCM_ERR_CUDA,
+                    std::string("templates_create: ") + cudaGetErrorString(e));
+    }
+    *out = t;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_templates_release(fdcm_templates* t) {
+    delete t;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_templates_lengths(const fdcm_templates* t, float* lengths) {
+    if (!t || !lengths) return fail(FDCM_ERR_INVALID, "null argument");
+    std::memcpy(lengths, t->lengths.data(), t->lengths.size() * sizeof(float));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_template_lengths(const float* tl, const int32_t* off, int32_t T, float* lengths) {
+    if (T < 0 || !off || !lengths) return fail(FDCM_ERR_INVALID, "null argument");
+    for (int t = 0; t < T; ++t) {
+        const int L = off[t + 1] - off[t];
+        std::vector<float> len((size_t)L);
+        for (int i = 0; i < L; ++i) len[(size_t)i] = line_length(tl + 4 * ((size_t)off[t] + i));
+        lengths[t] = eigen_sum(len.data(), L);
+    }
+    return FDCM_OK;
+}
+
+// =============================================================================================
+// search
+// =============================================================================================
+static float penalty_denominator(int kind, float tau, float length) {
+    const float len = std::max(length, 1e-6f);                    // exponentialpenalty.cpp:42
+    return kind == FDCM_PENALTY_DEFAULT ? len : std::pow(len, tau);   // defaultpenalty.cpp:39 / exponentialpenalty.cpp:43
+}
+
+extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, const float* scene, int32_t n_scene,
+                                   const fdcm_search_params* p, fdcm_match* out, int64_t capacity, int64_t* n_out) {
+    if (!m || !tc || !p || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (p->max_tmpl_lines < 0 || p->max_scene_lines < 0 || p->batch_size < 0 || p->top_k < 0 || p->penalty_kind < 0 ||
+        p->penalty_kind > 2)
+        return fail(FDCM_ERR_INVALID, "bad search parameters");
+    if (tc->device != m->device) return fail(FDCM_ERR_INVALID, "templates and feature map live on different devices");
+    fdcm_templates* t = const_cast<fdcm_templates*>(tc);
+    std::lock_guard<std::mutex> lk(m->search_mutex);
+    m->last_n_hyp = 0;
+    m->last_stats = fdcm_search_stats{0, 0, 0, 0};
+    // defaultmatch.cpp:40-41
+    if (t->n_tmpl == 0 || n_scene <= 0 || (m->dm.W == 0 && m->dm.H == 0)) return FDCM_OK;
+    if (!scene) return fail(FDCM_ERR_INVALID, "scene is null");
+    if (m->stage != 0) return fail(FDCM_ERR_INVALID, "feature map was built with a debug stage");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+
+    // ---- host prep: scene length order (defaultsearch.cpp:32-36) and hypothesis offsets ----
+    std::vector<float> slen((size_t)n_scene);
+    for (int i = 0; i < n_scene; ++i) slen[(size_t)i] = line_length(scene + 4 * (size_t)i);
+    const std::vector<long> sidx = argsort_desc(slen.data(), n_scene);
+    std::vector<float> sorted_len((size_t)n_scene);
+    std::vector<int32_t> sorted_idx((size_t)n_scene);
+    for (int i = 0; i < n_scene; ++i) {
+        sorted_len[(size_t)i] = slen[(size_t)sidx[(size_t)i]];
+        sorted_idx[(size_t)i] = (int32_t)sidx[(size_t)i];
+    }
+    const int nS = std::min<int>(n_scene, p->max_scene_lines);
+    std::vector<int64_t> hyp_off((size_t)t->n_tmpl + 1, 0);
+    for (int i = 0; i < t->n_tmpl; ++i) {
+        const int L = t->offsets[(size_t)i + 1] - t->offsets[(size_t)i];
+        hyp_off[(size_t)i + 1] = hyp_off[(size_t)i] + 2LL * std::min(L, p->max_tmpl_lines) * nS;
+    }
+    const int64_t H = hyp_off[(size_t)t->n_tmpl];
+    m->last_n_hyp = H;
+    m->last_stats.n_hypotheses = H;
+    if (H == 0) return FDCM_OK;
+
+    // penalty denominators (host powf, like the reference) cached per (kind, tau)
+    const float* d_denom = nullptr;
+    if (p->penalty_kind != FDCM_PENALTY_NONE) {
+        std::lock_guard<std::mutex> lk2(t->mu);
+        if (t->denom_kind != p->penalty_kind || t->denom_tau != p->penalty_tau) {
+            std::vector<float> den((size_t)t->n_tmpl);
+            for (int i = 0; i < t->n_tmpl; ++i) den[(size_t)i] = penalty_denominator(p->penalty_kind, p->penalty_tau, t->lengths[(size_t)i]);
+            CUDA_TRY(cudaMemcpyAsync(t->denom.p, den.data(), den.size() * 4, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+            t->denom_kind = p->penalty_kind;
+            t->denom_tau = p->penalty_tau;
+        }
+        d_denom = t->denom.as<float>();
+    }
+
+    // ---- workspace ----
+    CUDA_TRY(m->s_scene.reserve((size_t)n_scene * 16));
+    CUDA_TRY(m->s_sorted_len.reserve((size_t)n_scene * 4));
+    CUDA_TRY(m->s_sorted_idx.reserve((size_t)n_scene * 4));
+    CUDA_TRY(m->s_hyp_off.reserve(hyp_off.size() * 8));
+    CUDA_TRY(m->s_rec.reserve((size_t)H * sizeof(fdcm_match)));
+    CUDA_TRY(m->s_valid.reserve((size_t)H));
+    CUDA_TRY(m->s_hyp.reserve((size_t)H * 16));
+    CUDA_TRY(m->s_counters.reserve(3 * 8));
+    CUDA_TRY(cudaMemcpyAsync(m->s_scene.p, scene, (size_t)n_scene * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, sorted_len.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, sorted_idx.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->s_hyp_off.p, hyp_off.data(), hyp_off.size() * 8, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemsetAsync(m->s_counters.p, 0, 3 * 8, s));
+
+    TemplatesView tv;
+    tv.lines = t->lines.as<float4>();
+    tv.offsets = t->offs.as<int32_t>();
+    tv.argsort = t->argsort.as<int32_t>();
+    tv.line_len = t->line_len.as<float>();
+    tv.denom = d_denom;
+    tv.n_tmpl = t->n_tmpl;
+    tv.max_lines = std::max(1, t->max_lines);
+    SceneView sv;
+    sv.lines = m->s_scene.as<float4>();
+    sv.sorted_len = m->s_sorted_len.as<float>();
+    sv.sorted_idx = m->s_sorted_idx.as<int32_t>();
+    sv.n = n_scene;
+    SearchLaunch sl;
+    sl.max_tmpl_lines = p->max_tmpl_lines;
+    sl.max_scene_lines = p->max_scene_lines;
+    sl.batch = p->batch_size > 0 ? p->batch_size : 1;   // DefaultOptimize == batches of one (defaultoptimize.cpp:49-64)
+    sl.tmpl_idx_base = p->tmpl_idx_base;
+    sl.hyp_off = m->s_hyp_off.as<int64_t>();
+    sl.n_hyp = H;
+    SearchOutputs so;
+    so.rec = m->s_rec.as<fdcm_match>();
+    so.valid = m->s_valid.as<uint8_t>();
+    so.hyp = m->s_hyp.as<int4>();
+    so.counters = m->s_counters.as<unsigned long long>();
+    {
+        KernelScope k("search", 0.0, s);
+        launch_search(map_view(m), m->table_dev, tv, sv, sl, so, s);
+    }
+    CUDA_TRY(cudaGetLastError());
+
+    unsigned long long counters[3] = {0, 0, 0};
+    fdcm_status result = FDCM_OK;
+    if (p->top_k > 0) {
+        const int k = p->top_k;
+        const int blocks = topk_ws_blocks(H);
+        CUDA_TRY(m->s_topk_score.reserve((size_t)blocks * k * 4));
+        CUDA_TRY(m->s_topk_idx.reserve((size_t)blocks * k * 8));
+        CUDA_TRY(m->s_topk_out.reserve((size_t)k * sizeof(fdcm_match)));
+        CUDA_TRY(m->s_topk_n.reserve(4));
+        {
+            KernelScope ks("topk", 0.0, s, 2);   // two kernels in this scope
+            launch_topk(so.rec, so.valid, H, k, m->s_topk_score.as<float>(), m->s_topk_idx.as<int64_t>(), blocks,
+                        m->s_topk_out.as<fdcm_match>(), m->s_topk_n.as<int>(), s);
+        }
+        CUDA_TRY(cudaGetLastError());
+        int n_sel = 0;
+        std::vector<fdcm_match> sel((size_t)k);
+        CUDA_TRY(cudaMemcpyAsync(&n_sel, m->s_topk_n.p, 4, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(sel.data(), m->s_topk_out.p, (size_t)k * sizeof(fdcm_match), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(counters, m->s_counters.p, 3 * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        *n_out = n_sel;
+        if (n_sel > capacity || (n_sel > 0 && !out)) result = fail(FDCM_ERR_CAPACITY, "output buffer too small");
+        else if (n_sel > 0) std::memcpy(out, sel.data(), (size_t)n_sel * sizeof(fdcm_match));
+    } else {
+        // every match in hypothesis order: download records + flags, compact on the host
+        const size_t need = (size_t)H * sizeof(fdcm_match) + (size_t)H;
+        if (m->h_pinned_cap < need) {
+            if (m->h_pinned) cudaFreeHost(m->h_pinned);
+            m->h_pinned = nullptr;
+            m->h_pinned_cap = 0;
+            CUDA_TRY(cudaMallocHost(&m->h_pinned, need));
+            m->h_pinned_cap = need;
+        }
+        fdcm_match* h_rec = (fdcm_match*)m->h_pinned;
+        uint8_t* h_valid = (uint8_t*)m->h_pinned + (size_t)H * sizeof(fdcm_match);
+        CUDA_TRY(cudaMemcpyAsync(h_rec, so.rec, (size_t)H * sizeof(fdcm_match), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(h_valid, so.valid, (size_t)H, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(counters, m->s_counters.p, 3 * 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        int64_t n = 0;
+        for (int64_t h = 0; h < H; ++h) n += h_valid[h] ? 1 : 0;
+        *n_out = n;
+        if (n > capacity || (n > 0 && !out)) result = fail(FDCM_ERR_CAPACITY, "output buffer too small");
+        else {
+            int64_t w = 0;
+            for (int64_t h = 0; h < H; ++h)
+                if (h_valid[h]) out[w++] = h_rec[h];
+        }
+    }
+    prof_resolve();
+    m->last_stats.n_evaluations = (int64_t)counters[0];
+    m->last_stats.n_lookups = (int64_t)counters[1];
+    m->last_stats.n_valid = (int64_t)counters[2];
+    return result;
+}
+
+extern "C" fdcm_status fdcm_search_host(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                                        const float* scene, int32_t n_scene, const fdcm_search_params* p, fdcm_match* out,
+                                        int64_t capacity, int64_t* n_out) {
+    if (!m || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (n_tmpl <= 0) return FDCM_OK;
+    fdcm_templates* t = nullptr;
+    fdcm_status st = fdcm_templates_create(tmpl_lines, tmpl_offsets, n_tmpl, m->device, &t);
+    if (st != FDCM_OK) return st;
+    st = fdcm_search(m, t, scene, n_scene, p, out, capacity, n_out);
+    fdcm_templates_release(t);
+    return st;
+}
+
+extern "C" fdcm_status fdcm_search_last_hypotheses(const fdcm_dt3* m, int32_t* out, int64_t capacity, int64_t* n_out) {
+    if (!m || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(m->search_mutex);
+    *n_out = m->last_n_hyp;
+    if (m->last_n_hyp == 0) return FDCM_OK;
+    if (capacity < m->last_n_hyp || !out) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
+    CUDA_TRY(cudaSetDevice(m->device));
+    CUDA_TRY(cudaMemcpy(out, m->s_hyp.p, (size_t)m->last_n_hyp * 16, cudaMemcpyDeviceToHost));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_search_last_stats(const fdcm_dt3* m, fdcm_search_stats* stats) {
+    if (!m || !stats) return fail(FDCM_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(m->search_mutex);
+    *stats = m->last_stats;
+    return FDCM_OK;
+}
+
+// =============================================================================================
+// host-side helpers mirroring the remaining concept entry points (no device work)
+// =============================================================================================
+extern "C" fdcm_status fdcm_default_search(const float* tmpl, int32_t L, const float* scene, int32_t M, int32_t maxT, int32_t maxS,
+                                           int32_t* out_pairs, int32_t capacity, int32_t* n_out) {
+    if (!n_out || L < 0 || M < 0 || maxT < 0 || maxS < 0) return fail(FDCM_ERR_INVALID, "bad argument");
+    *n_out = 0;
+    if (L == 0 || M == 0) return FDCM_OK;
+    if (!tmpl || !scene) return fail(FDCM_ERR_INVALID, "null argument");
+    std::vector<float> sl((size_t)M), tl((size_t)L);
+    for (int i = 0; i < M; ++i) sl[(size_t)i] = line_length(scene + 4 * (size_t)i);
+    for (int i = 0; i < L; ++i) tl[(size_t)i] = line_length(tmpl + 4 * (size_t)i);
+    const std::vector<long> ss = argsort_desc(sl.data(), M), st = argsort_desc(tl.data(), L);
+    std::vector<float> sorted_len((size_t)M);
+    for (int i = 0; i < M; ++i) sorted_len[(size_t)i] = sl[(size_t)ss[(size_t)i]];
+    int32_t n = 0;
+    for (int r = 0; r < std::min(L, maxT); ++r) {
+        const long ti = st[(size_t)r];
+        const int64_t c = closest_in_descending(sorted_len.data(), M, tl[(size_t)ti]);
+        int64_t b, e;
+        centered_range(c, M, maxS, b, e);
+        for (int64_t i = b; i < e; ++i) {
+            if (n < capacity && out_pairs) {
+                out_pairs[2 * n] = (int32_t)ti;
+                out_pairs[2 * n + 1] = (int32_t)ss[(size_t)i];
+            }
+            ++n;
+        }
+    }
+    *n_out = n;
+    if (n > capacity) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_penalize(int32_t kind, float tau, fdcm_match* matches, int64_t n, const float* lengths, int64_t n_lengths) {
+    if (n < 0 || (n > 0 && !matches)) return fail(FDCM_ERR_INVALID, "bad matches");
+    if (kind != FDCM_PENALTY_DEFAULT && kind != FDCM_PENALTY_EXPONENTIAL) return fail(FDCM_ERR_INVALID, "unknown penalty");
+    for (int64_t i = 0; i < n; ++i)
+        if ((uint64_t)(uint32_t)matches[i].tmpl_idx >= (uint64_t)n_lengths || matches[i].tmpl_idx < 0)
+            return fail(FDCM_ERR_OUT_OF_RANGE,
+                        "In penalize, the size of templatelengths is not consistent with match template indices");
+    for (int64_t i = 0; i < n; ++i) matches[i].score = matches[i].score / penalty_denominator(kind, tau, lengths[matches[i].tmpl_idx]);
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_sort_matches(fdcm_match* matches, int64_t n) {
+    if (n < 0 || (n > 0 && !matches)) return fail(FDCM_ERR_INVALID, "bad matches");
+    std::sort(matches, matches + n, [](const fdcm_match& a, const fdcm_match& b) { return a.score < b.score; });
+    return FDCM_OK;
+}

@@ -1,0 +1,70 @@
+// kernels.h — launcher declarations shared by the C-ABI layer (fdcm_api.cu)
+#pragma once
+#include "common.cuh"
+#include "../../include/fdcm_b200.h"
+
+namespace fdcm {
+
+// ---- dt3_kernels.cu ----
+void launch_raster(const float* d_lines, const int32_t* d_bins, int n_lines, const MapDims& dm, uint32_t* d_mask, cudaStream_t s);
+void launch_dt_col_exact(const uint32_t* d_mask, const MapDims& dm, uint16_t* d_g, cudaStream_t s);
+void launch_mask_to_float(const uint32_t* d_mask, const MapDims& dm, float* d_planes, cudaStream_t s);
+void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, float* d_planes, const MapDims& dm,
+                            void* d_stack, cudaStream_t s);
+void launch_dt_row_l1(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s);
+void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s);
+void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, bool sqrt_first, cudaStream_t s);
+void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, cudaStream_t s);
+
+// ---- search_kernels.cu ----
+struct MapView {                 // read-only view of a built feature map
+    const float* planes;
+    MapDims dm;
+    float shift_x, shift_y;      // sceneTranslation (dt3cpu.h:56)
+};
+
+struct TemplatesView {
+    const float4* lines;         // all template lines, CSR by offsets
+    const int32_t* offsets;      // n_tmpl + 1
+    const int32_t* argsort;      // per template: line indices by descending length (std::sort order)
+    const float* line_len;       // per line length
+    const float* denom;          // per template penalty denominator (or nullptr)
+    int32_t n_tmpl;
+    int32_t max_lines;           // longest template
+};
+
+struct SceneView {
+    const float4* lines;         // original (un-shifted) scene lines
+    const float* sorted_len;     // lengths, descending (std::sort order of the reference comparator)
+    const int32_t* sorted_idx;   // scene line index of each sorted entry
+    int32_t n;
+};
+
+struct SearchLaunch {
+    int32_t max_tmpl_lines, max_scene_lines, batch;
+    int32_t tmpl_idx_base;
+    const int64_t* hyp_off;      // n_tmpl + 1 prefix of hypothesis counts
+    int64_t n_hyp;
+};
+
+struct SearchOutputs {
+    fdcm_match* rec;             // n_hyp records
+    uint8_t* valid;              // n_hyp flags (0 = nullopt)
+    int4* hyp;                   // n_hyp (tmpl, tmpl_line, scene_line, rev)
+    unsigned long long* counters;// [0] evaluations, [1] lookups, [2] valid
+};
+
+void launch_search(const MapView& map, const SlopeTableDev& table, const TemplatesView& tv, const SceneView& sv,
+                   const SearchLaunch& sl, const SearchOutputs& out, cudaStream_t s);
+
+// top-K smallest (score, index) among valid records; returns via d_out (k records) and d_n_out
+void launch_topk(const fdcm_match* d_rec, const uint8_t* d_valid, int64_t n, int k, float* d_ws_score, int64_t* d_ws_idx,
+                 int ws_blocks, fdcm_match* d_out, int* d_n_out, cudaStream_t s);
+int topk_ws_blocks(int64_t n);
+
+void launch_evaluate(const MapView& map, const SlopeTableDev& table, const float4* d_lines, const int32_t* d_toff,
+                     const float2* d_transl, const int32_t* d_troff, const int32_t* d_owner, int64_t n_scores,
+                     float* d_scores, cudaStream_t s);
+void launch_classify(const SlopeTableDev& table, const float4* d_lines, int n, int32_t* d_bins, cudaStream_t s);
+
+}   // namespace fdcm

@@ -1,0 +1,210 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libfdcm_b200.so) against the CPU oracle on the
+same seeded inputs, stage by stage.  Bars (BASELINE.json north_star): edge masks,
+orientation bins and hypothesis sets bit-exact; DT3 values within 1e-5 relative; scores within 1e-4
+relative; identical top-10.  In practice every stage is bit-exact and the tests assert that first,
+falling back to the stated tolerance only in the message.
+"""
+import numpy as np
+import pytest
+
+import openfdcm_b200 as fdcm
+from oracle import fdcm_oracle as orc
+from tests.util import F32, load_kats, plant_instances, synth_scene, synth_templates
+
+pytestmark = pytest.mark.gpu
+DIST = {"L2": (fdcm.distance.L2, orc.L2), "L2_SQUARED": (fdcm.distance.L2_SQUARED, orc.L2_SQUARED),
+        "L1": (fdcm.distance.L1, orc.L1)}
+KATS = load_kats()
+
+
+def _assert_planes(gpu_map, cpu_map, what, rtol=1e-5):
+    assert (gpu_map.width, gpu_map.height, gpu_map.depth) == (cpu_map.W, cpu_map.H, cpu_map.depth)
+    assert np.array_equal(gpu_map.angles(), cpu_map.keys)
+    for d in range(cpu_map.depth):
+        g, c = gpu_map.plane(d), cpu_map.plane(d)
+        if not np.array_equal(g, c):
+            bad = ~np.isclose(g, c, rtol=rtol, atol=0)
+            assert not bad.any(), f"{what}: plane {d}: {bad.sum()} values beyond rtol={rtol}, max abs diff {np.abs(g - c).max()}"
+            pytest.fail(f"{what}: plane {d} within tolerance but not bit-exact ({(g != c).sum()} values differ)")
+
+
+@pytest.mark.parametrize("dist", ["L2", "L2_SQUARED", "L1"])
+@pytest.mark.parametrize("stage", [1, 2, 0], ids=["dt", "propagated", "integral"])
+def test_build_stages_small(dist, stage):
+    scene = synth_scene(320, 240, 60, seed=11)
+    gd, od = DIST[dist]
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5, gd), stage=stage)
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5, od, stage=stage)
+    assert g.info.exact_dt_path == 1
+    assert np.allclose(g.get_scene_translation(), c.shift, rtol=0, atol=0)
+    _assert_planes(g, c, f"{dist} stage {stage}")
+
+
+def test_edge_masks_and_bins_bit_exact():
+    scene = synth_scene(640, 480, 300, seed=1000)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5, fdcm.distance.L2_SQUARED), stage=1)
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5, orc.L2_SQUARED, stage=1)
+    shifted = (scene.T.reshape(-1, 2) + c.shift).reshape(-1, 4).T.astype(F32)
+    bins = np.array([orc.closest_orientation(c.keys, shifted[:, i]) for i in range(shifted.shape[1])])
+    assert np.array_equal(g.scene_bins(), bins)
+    for d in range(c.depth):
+        assert np.array_equal(g.mask(d), (c.plane(d) == 0).astype(np.uint8)), f"edge mask of plane {d}"
+
+
+@pytest.mark.parametrize("depth", [1, 4, 7, 30])
+def test_other_depths(depth):
+    scene = synth_scene(200, 150, 40, seed=5)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(depth, 3.0, 2.2, fdcm.distance.L2))
+    c = orc.Dt3Cpu(scene, depth, 3.0, 2.2, orc.L2)
+    _assert_planes(g, c, f"depth {depth}")
+
+
+@pytest.mark.parametrize("dist", ["L2", "L1"])
+def test_general_path_large_side(dist):
+    """side > 2897: float(q^2) is inexact, the literal (non integer-exact) DT path must be taken."""
+    scene = synth_scene(2000, 1500, 120, seed=21)
+    gd, od = DIST[dist]
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(3, 5.0, 1.5, gd))
+    c = orc.Dt3Cpu(scene, 3, 5.0, 1.5, od)
+    assert g.width == 3000 and g.info.exact_dt_path == 0
+    _assert_planes(g, c, f"general path {dist}")
+
+
+@pytest.mark.parametrize("case", KATS["dt3_golden_rows"], ids=lambda c: c["cite"])
+def test_reference_golden_rows_on_gpu(case):
+    scene = np.array(case["scene"], F32)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(case["depth"], case["coeff"], case["padding"]))
+    f = g.plane(int(g.classify(scene)[0]))
+    assert np.allclose(f[int(f.shape[0] / 2)], np.array(case["middle_row"], F32), rtol=0, atol=1e-5)
+
+
+def test_empty_scene():
+    g = fdcm.build_cuda_featuremap(np.zeros((4, 0), F32), fdcm.Dt3CudaParameters())
+    assert g.get_feature_size().tolist() == [0, 0] and g.depth == 0
+    assert fdcm.search(fdcm.DefaultMatch(), fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), g,
+                       [synth_templates(1, 5, 100, 1)[0]], np.zeros((4, 0), F32)) == []
+
+
+def test_classify_matches_host_atanf():
+    rng = np.random.default_rng(3)
+    scene = synth_scene(100, 100, 10, seed=2)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    n = 20000
+    ang = rng.uniform(-np.pi, np.pi, n)
+    ln = rng.uniform(0.5, 200, n)
+    p1 = rng.uniform(-500, 500, (2, n))
+    lines = np.vstack([p1, p1 + ln * np.vstack([np.cos(ang), np.sin(ang)])]).astype(F32)
+    lines[:, :200] = np.round(lines[:, :200])          # axis-aligned / degenerate slopes
+    lines[2, 200:230] = lines[0, 200:230]              # vertical: dx == 0
+    lines[2:, 230:240] = lines[:2, 230:240]            # null lines: 0/0
+    keys = g.angles()
+    want = np.array([orc.closest_orientation(keys, lines[:, i]) for i in range(n)])
+    assert np.array_equal(g.classify(lines), want)
+
+
+def _workload(seed, width=640, height=480, n_scene=300, n_tmpl=20, n_lines=30):
+    scene = synth_scene(width, height, n_scene, seed=seed)
+    tmpls = synth_templates(n_tmpl, n_lines, width, seed=seed + 1)
+    scene = plant_instances(scene, tmpls, width, height, seed=seed + 2)
+    return scene, tmpls
+
+
+def test_evaluate_and_minmax():
+    scene, tmpls = _workload(31, n_tmpl=6)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    rng = np.random.default_rng(9)
+    placed, trans = [], []
+    for t in tmpls:
+        placed.append((t.T.reshape(-1, 2) + np.array([320, 240], F32)).reshape(-1, 4).T.astype(F32))
+        trans.append(rng.uniform(-40, 40, (17, 2)).astype(F32))
+    got = fdcm.evaluate(g, placed, trans)
+    for t, tr, s in zip(placed, trans, got):
+        assert np.array_equal(s, c.evaluate(t, tr))
+        for v in ([1, 0], [0.3, -1], [-1, 0.5], [0, 0], [0, 1]):
+            a, b = fdcm.minmax_translation(g, t, v), c.minmax_translation(t, v)
+            assert np.array_equal(a, b, equal_nan=True)
+
+
+@pytest.mark.parametrize("batch", [10, 1, 0], ids=["BatchOptimize(10)", "BatchOptimize(1)", "DefaultOptimize"])
+def test_search_full_list_config1(batch):
+    """BASELINE config 1 (README example shape): every match compared, in hypothesis order."""
+    scene, tmpls = _workload(1000)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    opt = fdcm.BatchOptimize(batch) if batch else fdcm.DefaultOptimize()
+    got = fdcm.search_all(g, tmpls, scene, fdcm.DefaultSearch(4, 4), opt)
+    orc.stats_reset()
+    want, hyp = c.search(tmpls, scene, 4, 4, batch=batch, want_hyp=True)
+    evals, lookups = orc.stats_get()
+    assert np.array_equal(g.last_hypotheses(), hyp), "hypothesis set must be bit-exact"
+    st = g.last_search_stats()
+    assert st["n_hypotheses"] == len(hyp) == 20 * 4 * 4 * 2
+    assert (st["n_evaluations"], st["n_lookups"]) == (evals, lookups)
+    assert len(got) == len(want) == st["n_valid"]
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.allclose(got["score"], want["score"], rtol=1e-4, atol=0)
+    assert np.array_equal(got["transform"], want["transform"])
+    assert np.array_equal(got["score"], want["score"]), "scores within 1e-4 but not bit-exact"
+
+
+@pytest.mark.parametrize("dist", ["L2", "L2_SQUARED", "L1"])
+def test_search_top10(dist):
+    scene, tmpls = _workload(77, n_tmpl=40, n_lines=25)
+    gd, od = DIST[dist]
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5, gd))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5, od)
+    got = fdcm.search_topk(g, tmpls, scene, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
+    raw = c.search(tmpls, scene, 4, 4, batch=10)
+    pen = orc.penalize(1, 1.5, raw, orc.template_lengths(tmpls))
+    order = np.lexsort((np.arange(len(pen)), pen["score"]))[:10]   # ascending score, ties by hypothesis order
+    want = pen[order]
+    assert len(got) == 10
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.array_equal(got["transform"], want["transform"])
+    assert np.allclose(got["score"], want["score"], rtol=1e-4, atol=0)
+    assert np.array_equal(got["score"], want["score"])
+
+
+def test_reference_api_roundtrip():
+    """The reference README flow with the CUDA types (README.md:46-82)."""
+    scene, tmpls = _workload(5, n_tmpl=8)
+    fm = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(depth=30, dt3Coeff=5.0, padding=1.5), fdcm.ThreadPool(4))
+    matches = fdcm.search(fdcm.DefaultMatch(), fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10, fdcm.ThreadPool(4)), fm, tmpls, scene)
+    pen = fdcm.penalize(fdcm.ExponentialPenalty(tau=1.5), matches, fdcm.get_template_lengths(tmpls))
+    srt = fdcm.sort_matches(pen)
+    assert len(srt) == len(matches) > 0
+    assert all(srt[i].score <= srt[i + 1].score for i in range(len(srt) - 1))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    raw = c.search(tmpls, scene, 4, 4, batch=10)
+    want = orc.sort_matches(orc.penalize(1, 1.5, raw, orc.template_lengths(tmpls)))
+    assert np.array_equal(np.array([m.score for m in srt], F32), want["score"])
+    assert np.allclose(fdcm.get_template_lengths(tmpls), orc.template_lengths(tmpls), rtol=0, atol=0)
+    with pytest.raises(IndexError):
+        fdcm.penalize(fdcm.DefaultPenalty(), matches, [])
+
+
+def test_search_edge_cases():
+    scene, tmpls = _workload(8, n_tmpl=3)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    s, o = fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10)
+    assert fdcm.search(fdcm.DefaultMatch(), s, o, g, [], scene) == []
+    assert fdcm.search(fdcm.DefaultMatch(), s, o, g, [np.zeros((4, 0), F32)], scene) == []
+    # ragged: an empty template between real ones, a 2-line template (fewer lines than max_tmpl_lines),
+    # a template far outside the map (all hypotheses nullopt) and a degenerate (zero-length) line
+    ragged = [tmpls[0], np.zeros((4, 0), F32), tmpls[1][:, :2], (tmpls[2] * 50).astype(F32),
+              np.array([[1, 5], [1, 5], [1, 9], [1, 5]], F32)]
+    got = fdcm.search_all(g, ragged, scene, fdcm.DefaultSearch(4, 6), o)
+    want, hyp = c.search(ragged, scene, 4, 6, batch=10, want_hyp=True)
+    assert np.array_equal(g.last_hypotheses(), hyp)
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.array_equal(got["score"], want["score"], equal_nan=True)
+    assert np.array_equal(got["transform"], want["transform"], equal_nan=True)
+    # more scene slots than scene lines
+    tiny_scene = scene[:, :3]
+    g2 = fdcm.build_cuda_featuremap(tiny_scene, fdcm.Dt3CudaParameters(30, 5.0, 2.2))
+    c2 = orc.Dt3Cpu(tiny_scene, 30, 5.0, 2.2)
+    got = fdcm.search_all(g2, tmpls, tiny_scene, fdcm.DefaultSearch(4, 10), o)
+    want = c2.search(tmpls, tiny_scene, 4, 10, batch=10)
+    assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
