@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark (BASELINE.json): template matches/sec on the pose-estimation sweep
+(config 3: 5000 templates x 40 lines vs one 1080p scene, DefaultSearch(4,4), BatchOptimize(10),
+depth 30, coeff 5, padding 1.5, L2, ExponentialPenalty(1.5), top-10), plus the DT3 build ms of the
+same padded 1080p scene (config 2) for L2 / L2_SQUARED / L1.
+
+A step = one pass of the hot path over one batch: build the scene's DT3 map + search this rank's
+5000-template shard + top-10 (+ all-gather/merge of the ranks' top-10 when N > 1).  Weak scaling:
+every rank searches its own 5000 templates against the same scene (template sharding by tmpl_idx,
+each rank builds the map itself; no data-path collective besides the 320-byte top-K all-gather).
+
+  value : templates/s with scene lines + templates already resident in HBM (kernels + top-K readback)
+  e2e   : the same through the host-buffer C-ABI calls (pinned host lines in, matches out; H2D/D2H timed)
+  --impl reference : the CPU oracle (port of the reference, all host threads) on a bounded sample.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "template_matches_per_sec"
+UNIT = "templates/s"
+N_TMPL, N_TMPL_LINES, TOP_K = 5000, 40, 10
+SCENE_W, SCENE_H, N_SCENE = 1920, 1080, 2000
+DEPTH, COEFF, PADDING, TAU = 30, 5.0, 1.5, 1.5
+MAX_T, MAX_S, BATCH = 4, 4, 10
+CONFIG = {
+    "workload": "config3 pose sweep: 5000 templates x 40 lines per GPU vs one 1920x1080 scene (2000 lines + planted "
+                "instances), DefaultSearch(4,4), BatchOptimize(10), depth 30, coeff 5, padding 1.5, L2, "
+                "ExponentialPenalty(1.5), top-10; step = DT3 build (2880x2880x30) + search + top-K",
+    "sharding": "templates by tmpl_idx (weak: 5000 per GPU); every rank builds the scene map itself",
+    "l2_policy": "inputs larger than L2: the 995 MB map is rebuilt every step",
+}
+
+
+def make_workload(rank):
+    from tests.util import plant_instances, synth_scene, synth_templates
+    base = synth_templates(N_TMPL, N_TMPL_LINES, SCENE_W, seed=3001)               # rank 0's shard plants the instances
+    scene = plant_instances(synth_scene(SCENE_W, SCENE_H, N_SCENE, seed=3000), base, SCENE_W, SCENE_H, seed=3002)
+    tmpls = base if rank == 0 else synth_templates(N_TMPL, N_TMPL_LINES, SCENE_W, seed=3001 + 17 * rank)
+    return scene, tmpls
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for nm, v in zip(names, out[2:]):
+                    if v.strip().lower() == "active":
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.05)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=10)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def cpu_baseline_sample(scene, tmpls, sample_templates, nthreads=0):
+    """Oracle (port of the reference, ThreadPool decomposition) on a bounded sample: one full map build +
+    a search of `sample_templates` templates; extrapolated to the 5000-template job."""
+    from oracle import fdcm_oracle as orc
+    cores = nthreads or orc.hardware_concurrency()
+    t0 = time.perf_counter()
+    fm = orc.Dt3Cpu(scene, DEPTH, COEFF, PADDING, orc.L2, nthreads=cores)
+    t_build = time.perf_counter() - t0
+    sub = tmpls[:sample_templates]
+    t0 = time.perf_counter()
+    raw = fm.search(sub, scene, MAX_T, MAX_S, batch=BATCH, nthreads=cores)
+    pen = orc.penalize(1, TAU, raw, orc.template_lengths(sub))
+    orc.sort_matches(pen)
+    t_search = time.perf_counter() - t0
+    t_job = t_build + t_search * (N_TMPL / float(sample_templates))
+    return {"value": N_TMPL / t_job, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 full DT3 build ({t_build:.2f} s) + search/penalize/sort of {sample_templates} of the 5000 templates "
+                      f"({t_search:.3f} s), extrapolated linearly to 5000 templates",
+            "build_s": t_build, "search_sample_s": t_search}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    scene, tmpls = make_workload(0)
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        last = cpu_baseline_sample(scene, tmpls, 250)
+        if i >= args.warmup:
+            vals.append(last["value"])
+    value = float(np.mean(vals))
+    last["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * N_TMPL / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "cpu_baseline": last,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import openfdcm_b200 as fdcm
+    from openfdcm_b200 import distributed as fd
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    stream = torch.cuda.current_stream()
+    fdcm.set_stream(local_rank, stream.cuda_stream)
+
+    scene, tmpls = make_workload(rank)
+    searcher, optimizer, penalty = fdcm.DefaultSearch(MAX_T, MAX_S), fdcm.BatchOptimize(BATCH), fdcm.ExponentialPenalty(TAU)
+    params = fdcm.Dt3CudaParameters(DEPTH, COEFF, PADDING, fdcm.distance.L2, device=local_rank)
+    base = rank * N_TMPL
+
+    # pinned host copies of the inputs for the end-to-end arm
+    flat, off = fdcm._pack(tmpls)
+    h_lines = torch.from_numpy(flat).pin_memory()
+    h_off = torch.from_numpy(off).pin_memory()
+    h_scene = torch.from_numpy(fdcm._records(scene)).pin_memory()
+    h2d = h_lines.numel() * 4 + h_off.numel() * 4 + h_scene.numel() * 4
+    d2h = TOP_K * 32
+
+    fm = fdcm.build_cuda_featuremap(scene, params)
+    tset = fdcm.TemplateSet(tmpls, device=local_rank)
+
+    def merge(top):
+        return fd.allgather_topk(top, TOP_K, device=dev) if world > 1 else top
+
+    def step_resident():
+        fm.rerun()
+        return merge(fdcm.search_topk(fm, tset, None, searcher, optimizer, penalty, TOP_K, base))
+
+    def step_e2e():
+        import ctypes as C
+        L = fdcm.lib()
+        fdcm.check(L.fdcm_dt3_rebuild(fm._h, h_scene.data_ptr(), h_scene.shape[0]))
+        out = np.zeros(TOP_K, fdcm.MATCH_DTYPE)
+        n = C.c_int64(0)
+        p = fdcm._lib.SearchParams(MAX_T, MAX_S, BATCH, penalty.kind, penalty.tau, TOP_K, base)
+        fdcm.check(L.fdcm_search_host(fm._h, h_lines.data_ptr(), h_off.data_ptr(), N_TMPL, h_scene.data_ptr(), h_scene.shape[0],
+                                      C.byref(p), fdcm.ptr(out), TOP_K, C.byref(n)))
+        return merge(out[: n.value])
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            fdcm.profile(True, reset=True)
+        launches0 = fdcm.kernel_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = None
+        for _ in range(steps):
+            res = fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        launches = fdcm.kernel_launch_count() - launches0
+        prof = fdcm.profile_report() if profile else None
+        if profile:
+            fdcm.profile(False)
+        return float(ms.item()), res, launches, prof
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms_res, top_res, launches, prof = timed(step_resident, args.steps, args.warmup, profile=True)
+    stats = fm.last_search_stats()
+    ms_e2e, top_e2e, _, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.stop()
+
+    # DT3 build ms (config 2 metric) per distance, kernels only, same 1080p scene
+    build_ms = {}
+    for name, d in (("L2", fdcm.distance.L2), ("L2_SQUARED", fdcm.distance.L2_SQUARED), ("L1", fdcm.distance.L1)):
+        m2 = fm if name == "L2" else fdcm.build_cuda_featuremap(
+            scene, fdcm.Dt3CudaParameters(DEPTH, COEFF, PADDING, d, device=local_rank))
+        t, _, _, _ = timed(m2.rerun, 10, 3)
+        build_ms[name] = t / 10
+        if m2 is not fm:
+            del m2
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_res / args.steps
+    value = world * N_TMPL / (ms_step / 1e3)
+    e2e_value = world * N_TMPL / (ms_e2e / args.steps / 1e3)
+    assert top_res is not None and len(top_res) == TOP_K and np.array_equal(top_res["tmpl_idx"], top_e2e["tmpl_idx"])
+
+    # roofline of the dominant kernel of the timed (resident) steps
+    peak, peak_kind = measured_peak()
+    n_px_bytes = float(DEPTH) * fm.width * fm.height * 4
+    algo = {"search": 32.0 * stats["n_lookups"] + 32.0 * stats["n_valid"]}
+    kernels = {}
+    for name, v in prof.items():
+        avg_ms = v["total_ms"] / max(1, v["launches"])
+        by = algo.get(name, v["bytes_per_launch"])
+        kernels[name] = {"avg_ms": avg_ms, "launches": v["launches"], "algorithmic_bytes": by,
+                         "achieved_gbs": (by / (avg_ms * 1e-3) / 1e9) if avg_ms > 0 else None}
+    dom = max(kernels, key=lambda k: kernels[k]["avg_ms"] * kernels[k]["launches"])
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(dom)
+    except Exception:
+        pass
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": (kernels[dom]["achieved_gbs"] or 0.0) / peak, "traffic": traffic,
+                "share_of_step": kernels[dom]["avg_ms"] * kernels[dom]["launches"] / ms_res}
+    build_model = {"algorithmic_bytes_5N": 5 * n_px_bytes, "ms_L2": build_ms["L2"],
+                   "achieved_gbs": 5 * n_px_bytes / (build_ms["L2"] * 1e-3) / 1e9,
+                   "frac_of_peak": 5 * n_px_bytes / (build_ms["L2"] * 1e-3) / 1e9 / peak}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": CONFIG,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernels": kernels,
+            "dt3_build_ms": build_ms, "dt3_build_roofline": build_model,
+            "search_stats": stats, "lookups_per_s": stats["n_lookups"] / (kernels["search"]["avg_ms"] * 1e-3),
+            "top10": [[int(r["tmpl_idx"]), float(r["score"])] for r in top_res]}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample(scene, tmpls, 250)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -165,6 +165,12 @@ fdcm_status fdcm_default_search(const float* tmpl_xyxy, int32_t n_tmpl_lines, co
                                 int32_t max_tmpl_lines, int32_t max_scene_lines, int32_t* out_pairs, int32_t capacity,
                                 int32_t* n_out);
 
+/* Orientation bins (closestOrientation, dt3cpu.h:93-114, for the `depth` keys of dt3cpu.h:188-190) of n lines,
+ * computed on the host two ways: with libm atanf (what the reference does) and through the slope-threshold
+ * table the device kernels use.  Host-only parity hook: the two outputs must be identical. */
+fdcm_status fdcm_orientation_bins(int32_t depth, const float* lines_xyxy, int32_t n_lines, int32_t* bins_atanf,
+                                  int32_t* bins_table);
+
 /* penalize (penaltystrategies/{default,exponential}penalty.cpp) and sort_matches
  * (python/src/matching.cpp:302-307) on host match lists — O(#matches) host helpers */
 fdcm_status fdcm_penalize(int32_t penalty_kind, float tau, fdcm_match* matches, int64_t n, const float* lengths,

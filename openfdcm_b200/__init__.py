@@ -289,7 +289,7 @@ def _search_raw(featuremap, templates, scene, searcher, optimizer, penalty=None,
     if not isinstance(featuremap, Dt3Cuda):
         raise TypeError("the CUDA search needs a Dt3Cuda feature map (build_cuda_featuremap)")
     tset = templates if isinstance(templates, TemplateSet) else TemplateSet(templates, featuremap.device)
-    s = _records(scene)
+    s = None if scene is None else _records(scene)   # None: the scene the map was built from, already resident
     p = _lib.SearchParams(searcher.max_tmpl_lines, searcher.max_scene_lines, int(optimizer.batch_size),
                           0 if penalty is None else penalty.kind, 0.0 if penalty is None else float(penalty.tau),
                           int(top_k), int(tmpl_idx_base))
@@ -299,7 +299,8 @@ def _search_raw(featuremap, templates, scene, searcher, optimizer, penalty=None,
         1, searcher.max_scene_lines)
     out = np.zeros(max(cap, 1), MATCH_DTYPE)
     n = C.c_int64(0)
-    check(lib().fdcm_search(featuremap._h, tset._h, ptr(s), s.shape[0], C.byref(p), ptr(out), out.shape[0], C.byref(n)))
+    check(lib().fdcm_search(featuremap._h, tset._h, ptr(s), 0 if s is None else s.shape[0], C.byref(p), ptr(out),
+                            out.shape[0], C.byref(n)))
     return out[: n.value]
 
 

@@ -202,6 +202,7 @@ struct fdcm_dt3 {
     mutable std::mutex search_mutex;
     mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
         s_topk_out, s_topk_n;
+    mutable int32_t s_scene_n = 0;      // scene lines currently resident for the search (original, un-shifted)
     mutable int64_t last_n_hyp = 0;
     mutable fdcm_search_stats last_stats{};
     mutable void* h_pinned = nullptr;   // pinned staging for match download
@@ -216,6 +217,29 @@ struct fdcm_dt3 {
     }
 };
 
+// scene length ordering of establishSearchStrategy (defaultsearch.cpp:32-36) + upload of the original scene
+static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, int32_t n_scene, cudaStream_t s) {
+    std::vector<float> slen((size_t)n_scene);
+    for (int i = 0; i < n_scene; ++i) slen[(size_t)i] = line_length(scene + 4 * (size_t)i);
+    const std::vector<long> sidx = argsort_desc(slen.data(), n_scene);
+    std::vector<float> sorted_len((size_t)n_scene);
+    std::vector<int32_t> sorted_idx((size_t)n_scene);
+    for (int i = 0; i < n_scene; ++i) {
+        sorted_len[(size_t)i] = slen[(size_t)sidx[(size_t)i]];
+        sorted_idx[(size_t)i] = (int32_t)sidx[(size_t)i];
+    }
+    m->s_scene_n = 0;
+    CUDA_TRY(m->s_scene.reserve((size_t)n_scene * 16));
+    CUDA_TRY(m->s_sorted_len.reserve((size_t)n_scene * 4));
+    CUDA_TRY(m->s_sorted_idx.reserve((size_t)n_scene * 4));
+    CUDA_TRY(cudaMemcpyAsync(m->s_scene.p, scene, (size_t)n_scene * 16, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, sorted_len.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, sorted_idx.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // pageable temporaries
+    m->s_scene_n = n_scene;
+    return FDCM_OK;
+}
+
 static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s);
 
 // host preparation: shift, size, keys, bins (reference dt3cpu.h:180-193), then upload
@@ -223,6 +247,7 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     m->n_lines = n_lines;
     m->scene_bins.clear();
     if (n_lines == 0) {   // dt3cpu.h:180-181: empty map, translation (0,0), size (0,0)
+        m->s_scene_n = 0;
         m->dm = MapDims{0, 0, 0, 0, 0, 0};
         m->shift[0] = m->shift[1] = 0.f;
         m->keys.clear();
@@ -286,7 +311,9 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     CUDA_TRY(cudaMemcpyAsync(m->lines.p, ts.data(), (size_t)n_lines * 16, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(m->bins.p, m->scene_bins.data(), (size_t)n_lines * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaStreamSynchronize(s));   // ts / scene_bins are pageable temporaries
-    return FDCM_OK;
+    // keep the original scene resident for searches that pass scene == NULL
+    std::lock_guard<std::mutex> lk(m->search_mutex);
+    return upload_search_scene(m, scene, n_lines, s);
 }
 
 static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
@@ -703,23 +730,17 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     m->last_n_hyp = 0;
     m->last_stats = fdcm_search_stats{0, 0, 0, 0};
     // defaultmatch.cpp:40-41
+    const bool resident_scene = scene == nullptr;
+    if (resident_scene) n_scene = m->s_scene_n;
     if (t->n_tmpl == 0 || n_scene <= 0 || (m->dm.W == 0 && m->dm.H == 0)) return FDCM_OK;
-    if (!scene) return fail(FDCM_ERR_INVALID, "scene is null");
     if (m->stage != 0) return fail(FDCM_ERR_INVALID, "feature map was built with a debug stage");
     CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t s;
     if (fdcm_status st = get_stream(m->device, &s)) return st;
 
     // ---- host prep: scene length order (defaultsearch.cpp:32-36) and hypothesis offsets ----
-    std::vector<float> slen((size_t)n_scene);
-    for (int i = 0; i < n_scene; ++i) slen[(size_t)i] = line_length(scene + 4 * (size_t)i);
-    const std::vector<long> sidx = argsort_desc(slen.data(), n_scene);
-    std::vector<float> sorted_len((size_t)n_scene);
-    std::vector<int32_t> sorted_idx((size_t)n_scene);
-    for (int i = 0; i < n_scene; ++i) {
-        sorted_len[(size_t)i] = slen[(size_t)sidx[(size_t)i]];
-        sorted_idx[(size_t)i] = (int32_t)sidx[(size_t)i];
-    }
+    if (!resident_scene)
+        if (fdcm_status st = upload_search_scene(m, scene, n_scene, s)) return st;
     const int nS = std::min<int>(n_scene, p->max_scene_lines);
     std::vector<int64_t> hyp_off((size_t)t->n_tmpl + 1, 0);
     for (int i = 0; i < t->n_tmpl; ++i) {
@@ -747,17 +768,11 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     }
 
     // ---- workspace ----
-    CUDA_TRY(m->s_scene.reserve((size_t)n_scene * 16));
-    CUDA_TRY(m->s_sorted_len.reserve((size_t)n_scene * 4));
-    CUDA_TRY(m->s_sorted_idx.reserve((size_t)n_scene * 4));
     CUDA_TRY(m->s_hyp_off.reserve(hyp_off.size() * 8));
     CUDA_TRY(m->s_rec.reserve((size_t)H * sizeof(fdcm_match)));
     CUDA_TRY(m->s_valid.reserve((size_t)H));
     CUDA_TRY(m->s_hyp.reserve((size_t)H * 16));
     CUDA_TRY(m->s_counters.reserve(3 * 8));
-    CUDA_TRY(cudaMemcpyAsync(m->s_scene.p, scene, (size_t)n_scene * 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, sorted_len.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, sorted_idx.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(m->s_hyp_off.p, hyp_off.data(), hyp_off.size() * 8, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemsetAsync(m->s_counters.p, 0, 3 * 8, s));
 
@@ -912,6 +927,19 @@ extern "C" fdcm_status fdcm_default_search(const float* tmpl, int32_t L, const f
     }
     *n_out = n;
     if (n > capacity) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_orientation_bins(int32_t depth, const float* lines, int32_t n, int32_t* bins_atanf, int32_t* bins_table) {
+    if (depth < 1 || depth > kMaxDepth || n < 0 || (n > 0 && !lines)) return fail(FDCM_ERR_INVALID, "bad argument");
+    const std::vector<float> keys = angle_keys(depth);
+    const SlopeTable table = build_slope_table(keys.data(), (int)keys.size());
+    for (int i = 0; i < n; ++i) {
+        const float* l = lines + 4 * (size_t)i;
+        const float slope = (l[3] - l[1]) / (l[2] - l[0]);
+        if (bins_atanf) bins_atanf[i] = bin_of_slope(keys.data(), (int)keys.size(), slope);
+        if (bins_table) bins_table[i] = slope_table_lookup(table, slope);
+    }
     return FDCM_OK;
 }
 

@@ -1,0 +1,122 @@
+"""CPU-side tests of the product library: the C ABI loads and exports every symbol the header declares,
+and the host-only entry points (orientation bins via the slope table, DefaultSearch, penalties, sort,
+template lengths) agree with the oracle.  No kernel is launched here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import openfdcm_b200 as fdcm
+from openfdcm_b200 import _lib
+from oracle import fdcm_oracle as orc
+from tests.util import F32, create_lines, load_kats, synth_scene, synth_templates
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KATS = load_kats()
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fdcm_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(fdcm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/fdcm_b200.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+    assert sorted(_lib.SIGNATURES) == declared
+    assert lib.fdcm_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(_lib.Dt3Params) == 16
+    assert C.sizeof(_lib.SearchParams) == 28
+    assert C.sizeof(_lib.Dt3Info) == 40
+    assert C.sizeof(_lib.SearchStats) == 32
+    assert _lib.MATCH_DTYPE.itemsize == 32
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("device present")
+    with pytest.raises(fdcm.FdcmError) as e:
+        fdcm.build_cuda_featuremap(np.array([[0], [0], [5], [5]], F32))
+    assert e.value.status == _lib.FDCM_ERR_CUDA
+
+
+def test_product_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "openfdcm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", "Makefile")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "fdcm_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f
+
+
+@pytest.mark.parametrize("depth", [1, 2, 4, 7, 30, 64])
+def test_slope_table_reproduces_atanf_bins(depth):
+    rng = np.random.default_rng(depth)
+    n = 200000
+    ang = rng.uniform(-np.pi, np.pi, n)
+    ln = 10.0 ** rng.uniform(-3, 3, n)
+    lines = np.zeros((n, 4), F32)
+    lines[:, 2] = ln * np.cos(ang)
+    lines[:, 3] = ln * np.sin(ang)
+    # slopes at and next to every bin boundary, plus the special values
+    keys = orc.angle_keys(depth).astype(np.float64)
+    mids = np.concatenate([(keys[:-1] + keys[1:]) / 2, [keys[-1] + np.pi / depth / 2, -np.pi / 2, np.pi / 2]])
+    t = np.tan(mids).astype(F32)
+    near = np.concatenate([np.nextafter(t, F32(np.inf)), t, np.nextafter(t, F32(-np.inf))])
+    for k in range(1, 40):
+        near = np.concatenate([near, np.nextafter(near[-3 * len(t):], F32(np.inf))])
+    m = len(near)
+    lines[:m, 0] = 0; lines[:m, 1] = 0; lines[:m, 2] = 1; lines[:m, 3] = near
+    lines[m:m + 6] = [[0, 0, 0, 1], [0, 0, 0, -1], [0, 0, 0, 0], [0, 0, 1, 0], [0, 0, -1, 0], [0, 0, -0.0, 1]]
+    a, b = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    _lib.check(_lib.lib().fdcm_orientation_bins(depth, _lib.ptr(lines), n, _lib.ptr(a), _lib.ptr(b)))
+    assert np.array_equal(a, b)
+    want = np.array([orc.closest_orientation(orc.angle_keys(depth), lines[i]) for i in range(0, n, 97)])
+    assert np.array_equal(a[::97], want)
+
+
+def test_default_search_matches_oracle_including_length_ties():
+    c = KATS["default_search"]
+    got = fdcm.establish_search_strategy(fdcm.DefaultSearch(c["max_tmpl_lines"], c["max_scene_lines"]),
+                                         np.array(c["tmpl"], F32), np.array(c["scene"], F32))
+    assert len(got) == 4 and all(p in c["allowed"] for p in got.tolist())
+    scene = synth_scene(640, 480, 300, seed=4)
+    for tmpl in synth_templates(6, 30, 640, seed=5) + [create_lines(10, 10), create_lines(40, 100)]:   # createLines: all lengths tie
+        for mt, ms in ((4, 4), (16, 16), (3, 10), (50, 400)):
+            got = fdcm.establish_search_strategy(fdcm.DefaultSearch(mt, ms), tmpl, scene)
+            assert np.array_equal(got, orc.default_search(tmpl, scene, mt, ms))
+    assert len(fdcm.establish_search_strategy(fdcm.DefaultSearch(4, 4), np.zeros((4, 0), F32), scene)) == 0
+
+
+def test_penalize_sort_lengths_match_oracle():
+    tmpls = synth_templates(7, 23, 640, seed=9) + [np.zeros((4, 1), F32)]
+    assert np.array_equal(np.array(fdcm.get_template_lengths(tmpls), F32), orc.template_lengths(tmpls))
+    rng = np.random.default_rng(1)
+    m = np.zeros(500, fdcm.MATCH_DTYPE)
+    m["tmpl_idx"] = rng.integers(0, len(tmpls), 500)
+    m["score"] = rng.uniform(0, 100, 500).astype(F32)
+    m["score"][::7] = m["score"][0]                      # ties: std::sort order must agree
+    m["transform"] = rng.standard_normal((500, 6)).astype(F32)
+    lengths = orc.template_lengths(tmpls)
+    for pen, kind, tau in ((fdcm.DefaultPenalty(), 0, 0.0), (fdcm.ExponentialPenalty(1.45), 1, 1.45)):
+        got = fdcm.penalize(pen, m, lengths)
+        want = orc.penalize(kind, tau, m, lengths)
+        assert np.array_equal(got, want)
+        assert np.array_equal(fdcm.sort_matches(got), orc.sort_matches(want))
+    with pytest.raises(IndexError):
+        fdcm.penalize(fdcm.ExponentialPenalty(2.0), m, lengths[:2])
+    # Match-object flavour of the API (python/src/matching.cpp:266-307)
+    objs = [fdcm.Match(int(r["tmpl_idx"]), float(r["score"]), r["transform"]) for r in m[:20]]
+    srt = fdcm.sort_matches(fdcm.penalize(fdcm.DefaultPenalty(), objs, lengths))
+    assert [o.score for o in srt] == sorted(o.score for o in srt)
