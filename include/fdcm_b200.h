@@ -165,6 +165,11 @@ fdcm_status fdcm_default_search(const float* tmpl_xyxy, int32_t n_tmpl_lines, co
                                 int32_t max_tmpl_lines, int32_t max_scene_lines, int32_t* out_pairs, int32_t capacity,
                                 int32_t* n_out);
 
+/* Parity hook: run the horizontal L2^2 pass (second _distanceTransformColumnPassL2 call, core/imgproc.h:91-130)
+ * on n_rows arbitrary rows of u16 vertical distances g (0xFFFF = FLT_MAX), f = g*g.  literal = 1 selects the
+ * literal stack kernel, 0 the exact-regime warp kernel.  out: n_rows x n floats (squared distances). */
+fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows, int32_t n, int32_t literal, int32_t device, float* out);
+
 /* Orientation bins (closestOrientation, dt3cpu.h:93-114, for the `depth` keys of dt3cpu.h:188-190) of n lines,
  * computed on the host two ways: with libm atanf (what the reference does) and through the slope-threshold
  * table the device kernels use.  Host-only parity hook: the two outputs must be identical. */

@@ -67,6 +67,7 @@ SIGNATURES = {
     "fdcm_search_last_stats": (C.c_int, [_P, C.POINTER(SearchStats)]),
     "fdcm_default_search": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32,
                                       C.POINTER(C.c_int32)]),
+    "fdcm_debug_dt_rows": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
     "fdcm_orientation_bins": (C.c_int, [C.c_int32, _P, C.c_int32, _P, _P]),
     "fdcm_penalize": (C.c_int, [C.c_int32, C.c_float, _P, C.c_int64, _P, C.c_int64]),
     "fdcm_sort_matches": (C.c_int, [_P, C.c_int64]),

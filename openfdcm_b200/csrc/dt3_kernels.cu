@@ -217,6 +217,164 @@ __global__ void __launch_bounds__(128) dt_pass_literal_kernel(const uint16_t* __
     }
 }
 
+// =============================================================================================
+// K2b (exact regime): horizontal pass of the L2 / L2^2 transform, one warp per row, row in shared memory.
+//
+// In the exact regime (2*(side-1)^2 < 2^24) every quantity of the reference's second
+// _distanceTransformColumnPassL2 call (core/imgproc.h:91-130) is an exactly representable integer, so
+//   (1) the envelope it builds is the true lower envelope of the parabolas f[v] + (q-v)^2, f = g^2, and the
+//       vertex that owns an integer q is the LEFTMOST argmin_v f[v] + (q-v)^2 (`while (z[k+1] < q)` keeps
+//       the left parabola on a tie; FLT_MAX columns never own a pixel);
+//   (2) its in-place second loop computes out[q] = (u < q ? out[u] : f[u]) + (q-u)^2 with u = owner(q),
+//       a sum of integers, exact in any order.
+// owner() is non-decreasing in q, so it is found by divide and conquer: the owner of the midpoint of an
+// interval lies between the owners of its end points (equal end owners resolve the whole interval).
+// Lanes take one query each; brackets longer than kCoopLen are scanned by the whole warp.  The chained
+// values are then resolved in place, 32 pixels at a time, exactly like the reference's left-to-right sweep.
+// =============================================================================================
+constexpr uint32_t kBigF = 0x3FFFFFFFu;   // stands for FLT_MAX: never wins against a finite parabola
+constexpr int kCoopLen = 40;
+
+// leftmost argmin of f[v] + (q-v)^2 over v in [lo, hi], all 32 lanes cooperating
+__device__ __forceinline__ int coop_owner(const uint32_t* f, int q, int lo, int hi, int lane) {
+    unsigned long long best = ~0ull;
+    for (int v = lo + lane; v <= hi; v += 32) {
+        const int d = q - v;
+        const unsigned long long key = ((unsigned long long)(f[v] + (uint32_t)(d * d)) << 16) | (unsigned)v;
+        best = key < best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    return (int)(best & 0xFFFFu);
+}
+
+__global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
+                                                           MapDims dm, int n_rows_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps = blockDim.x >> 5;
+    const int n = dm.W;
+    uint32_t* f = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * dm.pitch;
+    uint16_t* owner = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warps * dm.pitch) +
+                      (size_t)warp * dm.pitch;
+    const int row = blockIdx.x * warps + warp;   // row of the [D*H][pitch] stack of planes
+    if (row >= n_rows_total) return;
+    const uint16_t* gin = g + (size_t)row * dm.pitch;
+    float* out = planes + (size_t)row * dm.pitch;
+
+    // ---- load g, f = g^2; first / last finite column ----
+    int cmin = 0x7fffffff, cmax = -1;
+    for (int x = lane * 2; x < n; x += 64) {
+        const uint32_t two = *reinterpret_cast<const uint32_t*>(gin + x);   // pitch is even: x+1 < pitch
+        const uint32_t g0 = two & 0xFFFFu, g1 = two >> 16;
+        f[x] = g0 == kNoEdge16 ? kBigF : g0 * g0;
+        if (g0 != kNoEdge16) { cmin = min(cmin, x); cmax = max(cmax, x); }
+        if (x + 1 < n) {
+            f[x + 1] = g1 == kNoEdge16 ? kBigF : g1 * g1;
+            if (g1 != kNoEdge16) { cmin = min(cmin, x + 1); cmax = max(cmax, x + 1); }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
+        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
+    }
+    if (cmax < 0) {   // no edge pixel in this plane: the row stays FLT_MAX (imgproc.h:174)
+        for (int x = lane; x < n; x += 32) out[x] = FLT_MAX;
+        return;
+    }
+    __syncwarp();
+
+    // ---- owners by divide and conquer ----
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int s = P; s >= 1; s >>= 1) {
+        // queries of this level: q = s-1 + 2s*j < n (q+1 = s * odd)
+        if (s - 1 >= n) continue;
+        const int nq = (n - (s - 1) + 2 * s - 1) / (2 * s);
+        if (nq < 32) {
+            for (int j = 0; j < nq; ++j) {
+                const int q = s - 1 + 2 * s * j;
+                const int lo = (q - s >= 0) ? owner[q - s] : cmin;
+                const int hi = (q + s < n) ? owner[q + s] : cmax;
+                const int o = (lo == hi) ? lo : coop_owner(f, q, lo, hi, lane);
+                if (lane == 0) owner[q] = (uint16_t)o;
+            }
+        } else {
+            for (int j0 = 0; j0 < nq; j0 += 32) {
+                const int j = j0 + lane;
+                const bool act = j < nq;
+                const int q = s - 1 + 2 * s * j;
+                int lo = 0, hi = 0;
+                if (act) {
+                    lo = (q - s >= 0) ? owner[q - s] : cmin;
+                    hi = (q + s < n) ? owner[q + s] : cmax;
+                }
+                const bool is_long = act && (hi - lo) > kCoopLen;
+                if (act && !is_long) {
+                    int arg = lo;
+                    if (hi > lo) {
+                        int d = q - lo;
+                        uint32_t best = f[lo] + (uint32_t)(d * d);
+                        for (int v = lo + 1; v <= hi; ++v) {
+                            d = q - v;
+                            const uint32_t c = f[v] + (uint32_t)(d * d);
+                            if (c < best) { best = c; arg = v; }
+                        }
+                    }
+                    owner[q] = (uint16_t)arg;
+                }
+                unsigned todo = __ballot_sync(0xffffffffu, is_long);
+                while (todo) {
+                    const int src = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                    const int qq = __shfl_sync(0xffffffffu, q, src);
+                    const int l2 = __shfl_sync(0xffffffffu, lo, src);
+                    const int h2 = __shfl_sync(0xffffffffu, hi, src);
+                    const int o = coop_owner(f, qq, l2, h2, lane);
+                    if (lane == 0) owner[qq] = (uint16_t)o;
+                }
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- chained values, in place, 32 pixels at a time (imgproc.h:122-128 incl. its aliasing) ----
+    for (int x0 = 0; x0 < n; x0 += 32) {
+        const int q = x0 + lane;
+        const bool act = q < n;
+        const int u = act ? owner[q] : 0;
+        const int d = q - u;
+        const uint32_t add = (uint32_t)(d * d);
+        uint32_t val = 0;
+        bool done = !act;
+        if (act && (u >= q || u < x0)) {   // right of q (not yet overwritten) or an earlier, finished chunk
+            val = f[u] + add;
+            done = true;
+        }
+        // owners inside this chunk and left of q: wait for that lane
+        unsigned pending = __ballot_sync(0xffffffffu, !done);
+        while (pending) {
+            const int src = act ? max(u - x0, 0) : 0;
+            const uint32_t sv = __shfl_sync(0xffffffffu, val, src);
+            const unsigned dn = __ballot_sync(0xffffffffu, done);
+            if (!done && ((dn >> src) & 1u)) {
+                val = sv + add;
+                done = true;
+            }
+            pending = __ballot_sync(0xffffffffu, !done);
+        }
+        __syncwarp();
+        if (act) f[q] = val;
+        __syncwarp();
+    }
+    // ---- store (values < 2^24: exact in fp32) ----
+    for (int x = lane; x < n; x += 32) out[x] = f[x] >= kBigF ? FLT_MAX : (float)f[x];
+}
+
 // K2b (L1): second pass of the L1 transform (core/imgproc.h:137-146,178-184) along x on the u16
 // vertical distance; integers are exact, so min-plus order is irrelevant.
 __global__ void __launch_bounds__(128) dt_row_l1_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
@@ -390,6 +548,18 @@ void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, f
         dt_pass_literal_kernel<true><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
     else
         dt_pass_literal_kernel<false><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
+}
+
+void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {
+    const int warps = 4;
+    const size_t smem = (size_t)warps * dm.pitch * (sizeof(uint32_t) + sizeof(uint16_t));
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dt_row_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        attr_set = true;
+    }
+    const int rows = dm.D * dm.H;
+    dt_row_exact_kernel<<<cdiv(rows, warps), warps * 32, smem, s>>>(d_g, d_planes, dm, rows);
 }
 
 void launch_dt_row_l1(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {

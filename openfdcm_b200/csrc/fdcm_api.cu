@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -190,6 +191,7 @@ struct fdcm_dt3 {
     MapDims dm{};
     float shift[2] = {0.f, 0.f};
     bool exact = true;
+    bool row_literal = false;   // FDCM_ROW_LITERAL=1: use the literal row pass even in the exact regime (A/B testing)
     int n_lines = 0;
     std::vector<float> keys;
     std::vector<int32_t> scene_bins;
@@ -269,6 +271,10 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     m->dm = dm;
     // every intermediate of the reference's first/second L2 pass is an exact integer iff 2*(side-1)^2 < 2^24
     m->exact = 2.0 * (double)(dm.W - 1) * (double)(dm.W - 1) < 16777216.0;
+    {
+        const char* e = std::getenv("FDCM_ROW_LITERAL");
+        m->row_literal = e && e[0] == '1';
+    }
 
     // translated scene (core/math.h:352-354) and orientation bins with the host libm (dt3cpu.h:123-134)
     std::vector<float> ts((size_t)4 * n_lines);
@@ -338,9 +344,12 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
         if (dist == FDCM_L1) {
             KernelScope k("dt_row_l1", N / 2 + N, s);
             launch_dt_row_l1(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
-        } else {
+        } else if (m->row_literal) {
             KernelScope k("dt_row_literal", N / 2 + N, s);
             launch_dt_pass_literal(true, true, m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->stack.p, s);
+        } else {
+            KernelScope k("dt_row_exact", N / 2 + N, s);
+            launch_dt_row_exact(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
         }
     } else {
         {
@@ -927,6 +936,34 @@ extern "C" fdcm_status fdcm_default_search(const float* tmpl, int32_t L, const f
     }
     *n_out = n;
     if (n > capacity) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows, int32_t n, int32_t literal, int32_t device, float* out) {
+    if (!g_rows || !out || n_rows <= 0 || n <= 0 || n > 4000) return fail(FDCM_ERR_INVALID, "bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(device, &s)) return st;
+    MapDims dm;
+    dm.D = 1; dm.H = n_rows; dm.W = n; dm.pitch = (n + 31) / 32 * 32; dm.wwords = dm.pitch / 32;
+    dm.plane_elems = (size_t)dm.H * dm.pitch;
+    DevBuf dg, dp, ds;
+    cudaError_t e = dg.reserve(dm.plane_elems * 2);
+    if (e == cudaSuccess) e = dp.reserve(dm.plane_elems * 4);
+    if (e == cudaSuccess) e = ds.reserve(dm.plane_elems * 8);
+    if (e == cudaSuccess) e = cudaMemset(dg.p, 0xFF, dm.plane_elems * 2);
+    if (e == cudaSuccess) e = cudaMemcpy2D(dg.p, (size_t)dm.pitch * 2, g_rows, (size_t)n * 2, (size_t)n * 2, n_rows, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        KernelScope k(literal ? "dt_row_literal" : "dt_row_exact", 0.0, s);
+        if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
+        else launch_dt_row_exact(dg.as<uint16_t>(), dp.as<float>(), dm, s);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess) e = cudaMemcpy2D(out, (size_t)n * 4, dp.p, (size_t)dm.pitch * 4, (size_t)n * 4, n_rows, cudaMemcpyDeviceToHost);
+    prof_resolve();
+    dg.release(); dp.release(); ds.release();
+    if (e != cudaSuccess) return fail(FDCM_ERR_CUDA, std::string("debug_dt_rows: ") + cudaGetErrorString(e));
     return FDCM_OK;
 }
 

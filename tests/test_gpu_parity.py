@@ -208,3 +208,44 @@ def test_search_edge_cases():
     got = fdcm.search_all(g2, tmpls, tiny_scene, fdcm.DefaultSearch(4, 10), o)
     want = c2.search(tmpls, tiny_scene, 4, 10, batch=10)
     assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
+
+
+def _dt_rows(g, literal):
+    import ctypes as C
+    from openfdcm_b200 import _lib
+    g = np.ascontiguousarray(g, np.uint16)
+    out = np.zeros(g.shape, np.float32)
+    _lib.check(_lib.lib().fdcm_debug_dt_rows(_lib.ptr(g), g.shape[0], g.shape[1], int(literal), 0, _lib.ptr(out)))
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 64, 100, 1024, 2048, 2880, 2897])
+def test_row_pass_exact_kernel_vs_literal_oracle(n):
+    """The exact-regime warp kernel (leftmost-argmin owners + in-place chain) against the literal
+    imgproc.h:91-130 restatement on adversarial rows: many ties, plateaus, steep ramps, sparse columns."""
+    rng = np.random.default_rng(n)
+    rows = []
+    big = 0xFFFF
+    rows.append(np.zeros(n))                                   # all edges
+    rows.append(np.full(n, big))                               # no edge at all
+    rows.append(np.where(np.arange(n) == n // 2, 0, big))      # a single finite column
+    rows.append(np.arange(n) % 7)                              # periodic ties
+    rows.append(np.abs(np.arange(n) - n // 3))                 # 45-degree ramp: three-way ties everywhere
+    rows.append(np.minimum(np.arange(n) * 3, 2000))            # steep ramp (deep aliasing chains)
+    rows.append(np.minimum((np.arange(n)[::-1]) // 2, 2500))   # shallow ramp from the right
+    for k in range(40):
+        r = rng.integers(0, [3, 10, 50, 400, 2800][k % 5], n)
+        if k % 3 == 0:
+            r = np.where(rng.random(n) < 0.7, big, r)           # sparse finite columns
+        if k % 4 == 1:
+            r = np.repeat(r[:: 8], 8)[:n] if n >= 8 else r      # plateaus
+        rows.append(r)
+    g = np.stack([np.asarray(r).astype(np.int64)[:n] for r in rows]).astype(np.uint16)
+    got = _dt_rows(g, literal=False)
+    lit = _dt_rows(g, literal=True)
+    fmax = np.finfo(np.float32).max
+    for i in range(g.shape[0]):
+        f = np.where(g[i] == big, fmax, g[i].astype(np.float64) ** 2).astype(F32)
+        want = orc.dt_pass_l2_1d(f)
+        assert np.array_equal(lit[i], want), f"literal kernel row {i}"
+        assert np.array_equal(got[i], want), f"exact kernel row {i}: first diff at {np.flatnonzero(got[i] != want)[:5]}"
