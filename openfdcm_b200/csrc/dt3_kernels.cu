@@ -142,6 +142,85 @@ __global__ void __launch_bounds__(128) dt_col_exact_kernel(const uint32_t* __res
     }
 }
 
+// K2a, tiled: one CTA per (plane, 64 columns).  Phase A transposes the mask into per-column 32-row bit words
+// (warp ballots), phase B scans the bands once per column for the nearest edge above / below each band, phase C
+// resolves every pixel with two bit scans (clz / ffs) and writes 128-byte row segments of u16 distances.
+__global__ void __launch_bounds__(256) dt_col_tiled_kernel(const uint32_t* __restrict__ mask, MapDims dm,
+                                                           uint16_t* __restrict__ g, int nbands) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* M = reinterpret_cast<uint32_t*>(smem_raw);                  // [nbands][64] column bit words
+    int32_t* up_before = reinterpret_cast<int32_t*>(M + (size_t)nbands * 64);   // [nbands][64] last edge row above the band
+    int32_t* dn_after = up_before + (size_t)nbands * 64;                       // [nbands][64] first edge row below the band
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    const int d = blockIdx.y;
+    const int w0 = blockIdx.x * 2;                                        // first mask word (32 columns each)
+    const uint32_t* mp = mask + (size_t)d * dm.H * dm.wwords;
+    // ---- A: transpose ----
+    for (int b = warp; b < nbands; b += nwarps) {
+        const int y = b * 32 + lane;
+        uint32_t a0 = 0, a1 = 0;
+        if (y < dm.H) {
+            a0 = mp[(size_t)y * dm.wwords + w0];
+            if (w0 + 1 < dm.wwords) a1 = mp[(size_t)y * dm.wwords + w0 + 1];
+        }
+        uint32_t c0 = 0, c1 = 0;
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const uint32_t m0 = __ballot_sync(0xffffffffu, (a0 >> c) & 1u);
+            const uint32_t m1 = __ballot_sync(0xffffffffu, (a1 >> c) & 1u);
+            if (lane == c) { c0 = m0; c1 = m1; }
+        }
+        M[(size_t)b * 64 + lane] = c0;
+        M[(size_t)b * 64 + 32 + lane] = c1;
+    }
+    __syncthreads();
+    // ---- B: nearest edge row strictly above / below every band, per column ----
+    if (threadIdx.x < 64) {
+        const int c = threadIdx.x;
+        int last = -1;
+        for (int b = 0; b < nbands; ++b) {
+            up_before[(size_t)b * 64 + c] = last;
+            const uint32_t m = M[(size_t)b * 64 + c];
+            if (m) last = b * 32 + 31 - __clz(m);
+        }
+        int next = -1;
+        for (int b = nbands - 1; b >= 0; --b) {
+            dn_after[(size_t)b * 64 + c] = next;
+            const uint32_t m = M[(size_t)b * 64 + c];
+            if (m) next = b * 32 + __ffs(m) - 1;
+        }
+    }
+    __syncthreads();
+    // ---- C: per pixel ----
+    const int x = blockIdx.x * 64 + lane * 2;                             // this lane's two columns
+    if (x >= dm.pitch) return;
+    uint16_t* gp = g + (size_t)d * dm.plane_elems + x;
+    for (int b = warp; b < nbands; b += nwarps) {
+        const uint2 bits = *reinterpret_cast<const uint2*>(M + (size_t)b * 64 + lane * 2);
+        const int2 ub = *reinterpret_cast<const int2*>(up_before + (size_t)b * 64 + lane * 2);
+        const int2 da = *reinterpret_cast<const int2*>(dn_after + (size_t)b * 64 + lane * 2);
+        const int rows = min(32, dm.H - b * 32);
+        for (int r = 0; r < rows; ++r) {
+            const int y = b * 32 + r;
+            const uint32_t le = 0xFFFFFFFFu >> (31 - r), ge = 0xFFFFFFFFu << r;
+            uint32_t res = 0;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const uint32_t m = k ? bits.y : bits.x;
+                const int upb = k ? ub.y : ub.x, dna = k ? da.y : da.x;
+                const uint32_t above = m & le, below = m & ge;
+                const int up = above ? (b * 32 + 31 - __clz(above)) : upb;
+                const int dn = below ? (b * 32 + __ffs(below) - 1) : dna;
+                unsigned dist = 0xFFFFu;
+                if (up >= 0) dist = (unsigned)(y - up);
+                if (dn >= 0) dist = min(dist, (unsigned)(dn - y));
+                res |= (dist & 0xFFFFu) << (16 * k);
+            }
+            *reinterpret_cast<uint32_t*>(gp + (size_t)y * dm.pitch) = res;
+        }
+    }
+}
+
 // general regime: materialise the {0, FLT_MAX} image (core/imgproc.h:174-175)
 __global__ void __launch_bounds__(256) mask_to_float_kernel(const uint32_t* __restrict__ mask, MapDims dm,
                                                             float* __restrict__ planes) {
@@ -233,22 +312,46 @@ __global__ void __launch_bounds__(128) dt_pass_literal_kernel(const uint16_t* __
 // values are then resolved in place, 32 pixels at a time, exactly like the reference's left-to-right sweep.
 // =============================================================================================
 constexpr uint32_t kBigF = 0x3FFFFFFFu;   // stands for FLT_MAX: never wins against a finite parabola
-constexpr int kCoopLen = 40;
+constexpr int kScanLen = 48;              // brackets up to this length are scanned linearly
+constexpr int kMaxBlocks = 96;            // 32-column blocks per row (n <= 2897 -> 91)
 
-// leftmost argmin of f[v] + (q-v)^2 over v in [lo, hi], all 32 lanes cooperating
-__device__ __forceinline__ int coop_owner(const uint32_t* f, int q, int lo, int hi, int lane) {
-    unsigned long long best = ~0ull;
-    for (int v = lo + lane; v <= hi; v += 32) {
-        const int d = q - v;
-        const unsigned long long key = ((unsigned long long)(f[v] + (uint32_t)(d * d)) << 16) | (unsigned)v;
-        best = key < best ? key : best;
+// leftmost argmin of f[v] + (q-v)^2 over v in [lo, hi] by one lane.  Long brackets are pruned with the
+// per-32-column block minima (bmin: min f of the block, bpos: its leftmost position): a block can only hold
+// the owner if bmin + dist(q, block)^2 does not exceed the best cost already known.
+__device__ __forceinline__ int lane_owner(const uint32_t* f, const uint32_t* bmin, const uint16_t* bpos, int q, int lo, int hi) {
+    int d = q - lo;
+    uint32_t best = f[lo] + (uint32_t)(d * d);
+    int arg = lo;
+    if (hi - lo <= kScanLen) {
+        for (int v = lo + 1; v <= hi; ++v) {
+            d = q - v;
+            const uint32_t c = f[v] + (uint32_t)(d * d);
+            if (c < best) { best = c; arg = v; }
+        }
+        return arg;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = other < best ? other : best;
+    // upper bound from valid candidates: lo, hi and the minima of the blocks strictly inside the bracket
+    d = q - hi;
+    uint32_t U = min(best, f[hi] + (uint32_t)(d * d));
+    const int b_lo = lo >> 5, b_hi = hi >> 5;
+    for (int b = b_lo + 1; b < b_hi; ++b) {
+        d = q - (int)bpos[b];
+        U = min(U, bmin[b] + (uint32_t)(d * d));
     }
-    return (int)(best & 0xFFFFu);
+    // scan, left to right, every block whose lower bound does not exceed the bound (ties must be scanned)
+    best = 0xFFFFFFFFu;
+    for (int b = b_lo; b <= b_hi; ++b) {
+        const int v0 = max(b << 5, lo), v1 = min((b << 5) + 31, hi);
+        const int dist = q < v0 ? v0 - q : (q > v1 ? q - v1 : 0);
+        if (bmin[b] + (uint32_t)(dist * dist) > U) continue;
+        for (int v = v0; v <= v1; ++v) {
+            d = q - v;
+            const uint32_t c = f[v] + (uint32_t)(d * d);
+            if (c < best) { best = c; arg = v; }
+        }
+        U = min(U, best);
+    }
+    return arg;
 }
 
 __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
@@ -257,25 +360,28 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps = blockDim.x >> 5;
     const int n = dm.W;
-    uint32_t* f = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * dm.pitch;
-    uint16_t* owner = reinterpret_cast<uint16_t*>(reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warps * dm.pitch) +
-                      (size_t)warp * dm.pitch;
-    const int row = blockIdx.x * warps + warp;   // row of the [D*H][pitch] stack of planes
+    // per warp: f[pitch] u32 | bmin[96] u32 | owner[pitch] u16 | bpos[96] u16
+    const size_t per_warp = (size_t)dm.pitch * 6 + kMaxBlocks * 6;
+    unsigned char* base = smem_raw + (size_t)warp * per_warp;
+    uint32_t* f = reinterpret_cast<uint32_t*>(base);
+    uint32_t* bmin = f + dm.pitch;
+    uint16_t* owner = reinterpret_cast<uint16_t*>(bmin + kMaxBlocks);
+    uint16_t* bpos = owner + dm.pitch;
+    (void)warps;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // row of the [D*H][pitch] stack of planes
     if (row >= n_rows_total) return;
     const uint16_t* gin = g + (size_t)row * dm.pitch;
     float* out = planes + (size_t)row * dm.pitch;
 
     // ---- load g, f = g^2; first / last finite column ----
     int cmin = 0x7fffffff, cmax = -1;
-    for (int x = lane * 2; x < n; x += 64) {
-        const uint32_t two = *reinterpret_cast<const uint32_t*>(gin + x);   // pitch is even: x+1 < pitch
-        const uint32_t g0 = two & 0xFFFFu, g1 = two >> 16;
+    for (int x = lane * 2; x < dm.pitch; x += 64) {
+        const uint32_t two = *reinterpret_cast<const uint32_t*>(gin + x);
+        const uint32_t g0 = (x < n) ? (two & 0xFFFFu) : kNoEdge16, g1 = (x + 1 < n) ? (two >> 16) : kNoEdge16;
         f[x] = g0 == kNoEdge16 ? kBigF : g0 * g0;
+        f[x + 1] = g1 == kNoEdge16 ? kBigF : g1 * g1;
         if (g0 != kNoEdge16) { cmin = min(cmin, x); cmax = max(cmax, x); }
-        if (x + 1 < n) {
-            f[x + 1] = g1 == kNoEdge16 ? kBigF : g1 * g1;
-            if (g1 != kNoEdge16) { cmin = min(cmin, x + 1); cmax = max(cmax, x + 1); }
-        }
+        if (g1 != kNoEdge16) { cmin = min(cmin, x + 1); cmax = max(cmax, x + 1); }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -287,57 +393,31 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
         return;
     }
     __syncwarp();
+    // ---- per-block minima (lane = block, rotated column order: conflict-free) ----
+    const int nb = dm.pitch >> 5;
+    for (int b = lane; b < nb; b += 32) {
+        uint32_t m = 0xFFFFFFFFu;
+        int pos = 0;
+        for (int i = 0; i < 32; ++i) {
+            const int c = (i + lane) & 31;
+            const uint32_t v = f[(b << 5) + c];
+            if (v < m || (v == m && c < pos)) { m = v; pos = c; }
+        }
+        bmin[b] = m;
+        bpos[b] = (uint16_t)((b << 5) + pos);
+    }
+    __syncwarp();
 
     // ---- owners by divide and conquer ----
-    int P = 1;
-    while (P < n) P <<= 1;
-    for (int s = P; s >= 1; s >>= 1) {
-        // queries of this level: q = s-1 + 2s*j < n (q+1 = s * odd)
-        if (s - 1 >= n) continue;
-        const int nq = (n - (s - 1) + 2 * s - 1) / (2 * s);
-        if (nq < 32) {
-            for (int j = 0; j < nq; ++j) {
-                const int q = s - 1 + 2 * s * j;
-                const int lo = (q - s >= 0) ? owner[q - s] : cmin;
-                const int hi = (q + s < n) ? owner[q + s] : cmax;
-                const int o = (lo == hi) ? lo : coop_owner(f, q, lo, hi, lane);
-                if (lane == 0) owner[q] = (uint16_t)o;
-            }
-        } else {
-            for (int j0 = 0; j0 < nq; j0 += 32) {
-                const int j = j0 + lane;
-                const bool act = j < nq;
-                const int q = s - 1 + 2 * s * j;
-                int lo = 0, hi = 0;
-                if (act) {
-                    lo = (q - s >= 0) ? owner[q - s] : cmin;
-                    hi = (q + s < n) ? owner[q + s] : cmax;
-                }
-                const bool is_long = act && (hi - lo) > kCoopLen;
-                if (act && !is_long) {
-                    int arg = lo;
-                    if (hi > lo) {
-                        int d = q - lo;
-                        uint32_t best = f[lo] + (uint32_t)(d * d);
-                        for (int v = lo + 1; v <= hi; ++v) {
-                            d = q - v;
-                            const uint32_t c = f[v] + (uint32_t)(d * d);
-                            if (c < best) { best = c; arg = v; }
-                        }
-                    }
-                    owner[q] = (uint16_t)arg;
-                }
-                unsigned todo = __ballot_sync(0xffffffffu, is_long);
-                while (todo) {
-                    const int src = __ffs(todo) - 1;
-                    todo &= todo - 1;
-                    const int qq = __shfl_sync(0xffffffffu, q, src);
-                    const int l2 = __shfl_sync(0xffffffffu, lo, src);
-                    const int h2 = __shfl_sync(0xffffffffu, hi, src);
-                    const int o = coop_owner(f, qq, l2, h2, lane);
-                    if (lane == 0) owner[qq] = (uint16_t)o;
-                }
-            }
+    // level A: every 32nd pixel (q = 31, 63, ...) searched over the whole finite range [cmin, cmax]
+    for (int q = 31 + 32 * lane; q < n; q += 1024) owner[q] = (uint16_t)lane_owner(f, bmin, bpos, q, cmin, cmax);
+    __syncwarp();
+    // levels s = 16 .. 1: q+1 = s * odd, bracketed by the owners of q-s and q+s
+    for (int s = 16; s >= 1; s >>= 1) {
+        for (int q = s - 1 + 2 * s * lane; q < n; q += 64 * s) {
+            const int lo = (q - s >= 0) ? owner[q - s] : cmin;
+            const int hi = (q + s < n) ? owner[q + s] : cmax;
+            owner[q] = (uint16_t)((lo == hi) ? lo : lane_owner(f, bmin, bpos, q, lo, hi));
         }
         __syncwarp();
     }
@@ -466,52 +546,119 @@ __global__ void __launch_bounds__(128) propagate_generic_kernel(float* __restric
 // one thread per chain c carries the strictly sequential fp32 running sum (((a0+a1)+a2)+...).
 // y-major is the same with rows/columns swapped (and is the coalesced case for a [H][W] plane).
 // =============================================================================================
-__global__ void __launch_bounds__(128) integral_kernel(float* __restrict__ planes, MapDims dm,
-                                                       const __grid_constant__ IntegralParams ip) {
+// R(i) = (long)roundf(float(i) * r) per plane (r = ry for x-major, rx for y-major planes): the cumulative
+// minor-axis shift of a chain after i major-axis steps (sum of the reference's per-step deltas, imgproc.h:55,72)
+__global__ void integral_shift_table_kernel(int32_t* __restrict__ rtab, int len, const __grid_constant__ IntegralParams ip) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int d = blockIdx.y;
-    const int mode = ip.mode[d];
-    if (mode == 0) return;
+    if (i >= len) return;
+    const float r = ip.mode[d] == 1 ? ip.ry[d] : ip.rx[d];
+    rtab[(size_t)d * len + i] = (int32_t)round_to_ll((float)i * r);
+}
+
+// y-major planes: thread per chain, the row access of a warp is one coalesced 128-byte segment; 16 loads in
+// flight per thread hide the HBM latency (the running sum itself is the only serial dependency).
+__global__ void __launch_bounds__(128) integral_ymajor_kernel(float* __restrict__ planes, MapDims dm,
+                                                              const __grid_constant__ IntegralParams ip,
+                                                              const int32_t* __restrict__ rtab, int rlen) {
+    const int d = blockIdx.y;
+    if (ip.mode[d] != 2) return;
+    const int32_t* R = rtab + (size_t)d * rlen;
+    const float ry = ip.ry[d];
+    const int Rend = R[dm.H - 1];
+    const int cmin = Rend > 0 ? -Rend : 0;
+    const int cmax = (Rend < 0 ? -Rend : 0) + dm.W - 1;
+    const int c = cmin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > cmax) return;
+    // rows are visited at y = p0y + i*sy: fold the direction into a row pointer and a signed pitch
+    const long long rstep = ry < 0 ? -(long long)dm.pitch : (long long)dm.pitch;
+    float* row = planes + (size_t)d * dm.plane_elems + (ry < 0 ? (size_t)(dm.H - 1) * dm.pitch : 0);
+    float acc = 0.f;
+    bool have = false;
+    constexpr int U = 16;
+    for (int i0 = 0; i0 < dm.H; i0 += U) {
+        float a[U];
+        int xs[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            const int i = i0 + k;
+            const int x = (i < dm.H) ? c + __ldg(R + i) : -1;
+            xs[k] = ((unsigned)x < (unsigned)dm.W) ? x : -1;
+            a[k] = xs[k] >= 0 ? row[(long long)k * rstep + xs[k]] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (xs[k] >= 0) {
+                if (have) { acc = a[k] + acc; row[(long long)k * rstep + xs[k]] = acc; }
+                else { acc = a[k]; have = true; }
+            } else {
+                have = false;
+            }
+        }
+        row += (long long)U * rstep;
+    }
+}
+
+// x-major planes: a warp owns 32 consecutive chains and walks the columns in blocks of 32.  Each block is
+// staged through a shared-memory tile (<= 64 rows x 32 columns, row segments loaded / stored as coalesced
+// 128-byte pieces), lane j then runs chain j sequentially across the 32 columns of the tile.
+constexpr int kTileRows = 64, kTilePitch = 33;
+
+__global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict__ planes, MapDims dm,
+                                                              const __grid_constant__ IntegralParams ip,
+                                                              const int32_t* __restrict__ rtab, int rlen) {
+    __shared__ float tiles[4][kTileRows * kTilePitch];
+    const int d = blockIdx.y;
+    if (ip.mode[d] != 1) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile = tiles[warp];
     float* P = planes + (size_t)d * dm.plane_elems;
-    const float rx = ip.rx[d], ry = ip.ry[d];
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (mode == 2) {
-        // y-major: rows i = 0..H-1 at y_i = p0y + i*sy; chain c at x_i = c + R(i), R(i) = round(i*rx)
-        const int sy = (int)ry;
-        const int p0y = ry < 0 ? dm.H - 1 : 0;
-        const long long Rend = round_to_ll((float)(dm.H - 1) * rx);
-        const long long cmin = Rend > 0 ? -Rend : 0;
-        const long long cmax = (Rend < 0 ? -Rend : 0) + dm.W - 1;
-        const long long c = cmin + t;
-        if (c > cmax) return;
-        float acc = 0.f;
-        bool have = false;
-        for (int i = 0; i < dm.H; ++i) {
-            const long long x = c + round_to_ll((float)i * rx);
-            if (x < 0 || x >= dm.W) { have = false; continue; }
-            float* p = P + (size_t)(p0y + i * sy) * dm.pitch + x;
-            const float a = *p;
-            if (have) { acc = a + acc; *p = acc; }
-            else { acc = a; have = true; }
+    const int32_t* R = rtab + (size_t)d * rlen;
+    const float rx = ip.rx[d];
+    const int sx = rx < 0 ? -1 : 1;
+    const int p0x = rx < 0 ? dm.W - 1 : 0;
+    const int Rend = R[dm.W - 1];
+    const int cmin = Rend > 0 ? -Rend : 0;
+    const int cmax = (Rend < 0 ? -Rend : 0) + dm.H - 1;
+    const int c0 = cmin + (blockIdx.x * 4 + warp) * 32;                    // first chain of this warp
+    if (c0 > cmax) return;
+    float acc = 0.f;
+    bool have = false;
+    for (int i0 = 0; i0 < dm.W; i0 += 32) {
+        const int i = i0 + lane;                                           // this lane's column step (load/store role)
+        const bool col_ok = i < dm.W;
+        const int Rl = R[col_ok ? i : dm.W - 1];
+        const int Ra = __shfl_sync(0xffffffffu, Rl, 0);
+        const int Rb = __shfl_sync(0xffffffffu, Rl, min(31, dm.W - 1 - i0));
+        const int Rmin = min(Ra, Rb);
+        const int ybase = c0 + Rmin;
+        const int nrows = 32 + abs(Ra - Rb);
+        const int r_lo = max(0, -ybase), r_hi = min(nrows, dm.H - ybase);  // rows of the tile inside the image
+        const int off = col_ok ? Rl - Rmin : 0x40000000;                   // tile row of chain c0 in this lane's column
+        float* gp = P + (long long)(ybase + r_lo) * dm.pitch + (p0x + i * sx);
+        // ---- load: row r of the tile, lane = column; element belongs to chain (r - off) ----
+        for (int r = r_lo; r < r_hi; ++r, gp += dm.pitch)
+            if ((unsigned)(r - off) < 32u) tile[r * kTilePitch + lane] = *gp;
+        __syncwarp();
+        // ---- sequential sums: lane = chain ----
+        const int ncols = min(32, dm.W - i0);
+        for (int j = 0; j < ncols; ++j) {
+            const int r = lane + __shfl_sync(0xffffffffu, off, j);         // tile row of this lane's chain in column j
+            if (r >= r_lo && r < r_hi) {
+                float* t = tile + r * kTilePitch + j;
+                const float a = *t;
+                if (have) { acc = a + acc; *t = acc; }
+                else { acc = a; have = true; }
+            } else {
+                have = false;
+            }
         }
-    } else {
-        // x-major: columns i = 0..W-1 at x_i = p0x + i*sx; chain c at y_i = c + R(i), R(i) = round(i*ry)
-        const int sx = (int)rx;
-        const int p0x = rx < 0 ? dm.W - 1 : 0;
-        const long long Rend = round_to_ll((float)(dm.W - 1) * ry);
-        const long long cmin = Rend > 0 ? -Rend : 0;
-        const long long cmax = (Rend < 0 ? -Rend : 0) + dm.H - 1;
-        const long long c = cmin + t;
-        if (c > cmax) return;
-        float acc = 0.f;
-        bool have = false;
-        for (int i = 0; i < dm.W; ++i) {
-            const long long y = c + round_to_ll((float)i * ry);
-            if (y < 0 || y >= dm.H) { have = false; continue; }
-            float* p = P + (size_t)y * dm.pitch + (p0x + i * sx);
-            const float a = *p;
-            if (have) { acc = a + acc; *p = acc; }
-            else { acc = a; have = true; }
-        }
+        __syncwarp();
+        // ---- store ----
+        gp = P + (long long)(ybase + r_lo) * dm.pitch + (p0x + i * sx);
+        for (int r = r_lo; r < r_hi; ++r, gp += dm.pitch)
+            if ((unsigned)(r - off) < 32u) *gp = tile[r * kTilePitch + lane];
+        __syncwarp();
     }
 }
 
@@ -528,7 +675,19 @@ void launch_raster(const float* d_lines, const int32_t* d_bins, int n_lines, con
 }
 
 void launch_dt_col_exact(const uint32_t* d_mask, const MapDims& dm, uint16_t* d_g, cudaStream_t s) {
-    dim3 grid(cdiv(dm.W, 128), dm.D);
+    const int nbands = (dm.H + 31) / 32;
+    const size_t smem = (size_t)nbands * 64 * 12;
+    if (smem <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(dt_col_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        dim3 grid((dm.wwords + 1) / 2, dm.D);
+        dt_col_tiled_kernel<<<grid, 256, smem, s>>>(d_mask, dm, d_g, nbands);
+        return;
+    }
+    dim3 grid(cdiv(dm.W, 128), dm.D);   // very tall maps: one thread per column, two sweeps
     dt_col_exact_kernel<<<grid, 128, 0, s>>>(d_mask, dm, d_g);
 }
 
@@ -552,7 +711,7 @@ void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, f
 
 void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {
     const int warps = 4;
-    const size_t smem = (size_t)warps * dm.pitch * (sizeof(uint32_t) + sizeof(uint16_t));
+    const size_t smem = (size_t)warps * ((size_t)dm.pitch * 6 + 96 * 6);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(dt_row_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -581,9 +740,20 @@ void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, 
     }
 }
 
-void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, cudaStream_t s) {
+void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, int32_t* d_rtab, cudaStream_t s) {
+    const int rlen = dm.W > dm.H ? dm.W : dm.H;
+    {
+        dim3 tgrid(cdiv(rlen, 256), dm.D);
+        integral_shift_table_kernel<<<tgrid, 256, 0, s>>>(d_rtab, rlen, ip);
+    }
     dim3 grid(cdiv((size_t)dm.W + dm.H, 128), dm.D);   // #chains <= W + H
-    integral_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip);
+    bool any_x = false, any_y = false;
+    for (int d = 0; d < dm.D; ++d) {
+        any_x |= ip.mode[d] == 1;
+        any_y |= ip.mode[d] == 2;
+    }
+    if (any_y) integral_ymajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
+    if (any_x) integral_xmajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
 }
 
 }   // namespace fdcm

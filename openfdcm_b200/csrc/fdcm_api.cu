@@ -199,7 +199,7 @@ struct fdcm_dt3 {
     SlopeTableDev table_dev{};
     PropParams prop{};
     IntegralParams integ{};
-    DevBuf planes, mask, g, stack, lines, bins;
+    DevBuf planes, mask, g, stack, lines, bins, rtab;
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
     mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
@@ -212,7 +212,7 @@ struct fdcm_dt3 {
 
     ~fdcm_dt3() {
         cudaSetDevice(device);
-        for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
+        for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &rtab, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
                           &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n})
             b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
@@ -312,6 +312,7 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t)));
     if (m->exact) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
     if (m->params.distance != FDCM_L1) CUDA_TRY(m->stack.reserve(n_px * 8));
+    CUDA_TRY(m->rtab.reserve((size_t)D * std::max(dm.W, dm.H) * sizeof(int32_t)));
     CUDA_TRY(m->lines.reserve((size_t)n_lines * 16));
     CUDA_TRY(m->bins.reserve((size_t)n_lines * 4));
     CUDA_TRY(cudaMemcpyAsync(m->lines.p, ts.data(), (size_t)n_lines * 16, cudaMemcpyHostToDevice, s));
@@ -386,8 +387,8 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             launch_propagate(m->planes.as<float>(), dm, m->prop, need_sqrt, s);
         }
         if (m->stage == 0) {
-            KernelScope k("integral", 2 * N, s);
-            launch_integral(m->planes.as<float>(), dm, m->integ, s);
+            KernelScope k("integral", 2 * N, s, 3);
+            launch_integral(m->planes.as<float>(), dm, m->integ, m->rtab.as<int32_t>(), s);
         }
     }
     CUDA_TRY(cudaGetLastError());
@@ -951,16 +952,17 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
     cudaError_t e = dg.reserve(dm.plane_elems * 2);
     if (e == cudaSuccess) e = dp.reserve(dm.plane_elems * 4);
     if (e == cudaSuccess) e = ds.reserve(dm.plane_elems * 8);
-    if (e == cudaSuccess) e = cudaMemset(dg.p, 0xFF, dm.plane_elems * 2);
-    if (e == cudaSuccess) e = cudaMemcpy2D(dg.p, (size_t)dm.pitch * 2, g_rows, (size_t)n * 2, (size_t)n * 2, n_rows, cudaMemcpyHostToDevice);
+    // same stream as the kernel: legacy-stream copies do not order against a non-blocking stream
+    if (e == cudaSuccess) e = cudaMemsetAsync(dg.p, 0xFF, dm.plane_elems * 2, s);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(dg.p, (size_t)dm.pitch * 2, g_rows, (size_t)n * 2, (size_t)n * 2, n_rows, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
         KernelScope k(literal ? "dt_row_literal" : "dt_row_exact", 0.0, s);
         if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
         else launch_dt_row_exact(dg.as<uint16_t>(), dp.as<float>(), dm, s);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(out, (size_t)n * 4, dp.p, (size_t)dm.pitch * 4, (size_t)n * 4, n_rows, cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e == cudaSuccess) e = cudaMemcpy2D(out, (size_t)n * 4, dp.p, (size_t)dm.pitch * 4, (size_t)n * 4, n_rows, cudaMemcpyDeviceToHost);
     prof_resolve();
     dg.release(); dp.release(); ds.release();
     if (e != cudaSuccess) return fail(FDCM_ERR_CUDA, std::string("debug_dt_rows: ") + cudaGetErrorString(e));

@@ -15,7 +15,7 @@ void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm
 void launch_dt_row_l1(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, bool sqrt_first, cudaStream_t s);
-void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, cudaStream_t s);
+void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, int32_t* d_rtab, cudaStream_t s);
 
 // ---- search_kernels.cu ----
 struct MapView {                 // read-only view of a built feature map
