@@ -150,6 +150,13 @@ fdcm_status fdcm_templates_lengths(const fdcm_templates* t, float* lengths);
  * when FDCM_ERR_CAPACITY). */
 fdcm_status fdcm_search(const fdcm_dt3* map, const fdcm_templates* templates, const float* scene_xyxy, int32_t n_scene,
                         const fdcm_search_params* params, fdcm_match* out, int64_t capacity, int64_t* n_out);
+/* optimize(optimizer, templates, alignments, featuremap) (matching/optimizestrategy.h:62-64; BatchOptimize:
+ * batchoptimize.cpp:6-123, batch_size == 0: DefaultOptimize, defaultoptimize.cpp:6-93).  The templates are used
+ * as given (already aligned); alignments: n_tmpl (x,y) pairs.  Outputs per template: has_value (0 = nullopt),
+ * score and translation[2] (OptimalTranslation, optimizestrategy.h:34-38). */
+fdcm_status fdcm_optimize(const fdcm_dt3* map, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                          const float* alignments, int32_t batch_size, uint8_t* has_value, float* scores,
+                          float* translations);
 /* one-shot variant taking host templates (uploads, searches, frees) */
 fdcm_status fdcm_search_host(const fdcm_dt3* map, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
                              const float* scene_xyxy, int32_t n_scene, const fdcm_search_params* params,

@@ -21,7 +21,7 @@ __all__ = [
     "distance", "Dt3CudaParameters", "Dt3Cuda", "build_cuda_featuremap", "ThreadPool", "DefaultSearch",
     "BatchOptimize", "DefaultOptimize", "DefaultMatch", "DefaultPenalty", "ExponentialPenalty", "Match",
     "TemplateSet", "search", "search_topk", "penalize", "get_template_lengths", "sort_matches", "evaluate",
-    "minmax_translation", "get_feature_size", "establish_search_strategy", "FdcmError", "MATCH_DTYPE",
+    "minmax_translation", "get_feature_size", "establish_search_strategy", "optimize", "FdcmError", "MATCH_DTYPE",
 ]
 
 
@@ -371,6 +371,20 @@ def evaluate(featuremap, templates, translations):
     scores = np.zeros(int(troff[-1]), np.float32)
     check(lib().fdcm_dt3_evaluate(featuremap._h, ptr(flat), ptr(off), len(off) - 1, ptr(tflat), ptr(troff), ptr(scores)))
     return [scores[troff[i]:troff[i + 1]].copy() for i in range(len(tr))]
+
+
+def optimize(optimizer, templates, alignments, featuremap):
+    """matching::optimize (optimizestrategy.h:62-64): list of None | (score, translation[2]) per template."""
+    flat, off = _pack(templates)
+    al = np.ascontiguousarray(np.asarray(alignments, np.float32).reshape(-1, 2))
+    n = len(off) - 1
+    if al.shape[0] != n:
+        raise ValueError("templates and alignments must have the same length")
+    has = np.zeros(n, np.uint8)
+    sc = np.zeros(n, np.float32)
+    tr = np.zeros((n, 2), np.float32)
+    check(lib().fdcm_optimize(featuremap._h, ptr(flat), ptr(off), n, ptr(al), int(optimizer.batch_size), ptr(has), ptr(sc), ptr(tr)))
+    return [(float(sc[i]), tr[i].copy()) if has[i] else None for i in range(n)]
 
 
 def establish_search_strategy(searcher, tmpl, scene):

@@ -61,6 +61,7 @@ SIGNATURES = {
     "fdcm_templates_release": (C.c_int, [_P]),
     "fdcm_templates_lengths": (C.c_int, [_P, _P]),
     "fdcm_search": (C.c_int, [_P, _P, _P, C.c_int32, C.POINTER(SearchParams), _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "fdcm_optimize": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, _P, _P, _P]),
     "fdcm_search_host": (C.c_int, [_P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(SearchParams), _P, C.c_int64,
                                    C.POINTER(C.c_int64)]),
     "fdcm_search_last_hypotheses": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),

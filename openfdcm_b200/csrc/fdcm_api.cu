@@ -806,6 +806,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     sl.tmpl_idx_base = p->tmpl_idx_base;
     sl.hyp_off = m->s_hyp_off.as<int64_t>();
     sl.n_hyp = H;
+    sl.direct_align = nullptr;
     SearchOutputs so;
     so.rec = m->s_rec.as<fdcm_match>();
     so.valid = m->s_valid.as<uint8_t>();
@@ -872,6 +873,74 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     m->last_stats.n_lookups = (int64_t)counters[1];
     m->last_stats.n_valid = (int64_t)counters[2];
     return result;
+}
+
+// optimize(optimizer, templates, alignments, featuremap) (matching/optimizestrategy.h:62-64;
+// batchoptimize.cpp:6-123 / defaultoptimize.cpp:6-93): the templates are taken as given (already aligned).
+extern "C" fdcm_status fdcm_optimize(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                                     const float* alignments, int32_t batch_size, uint8_t* has_value, float* scores,
+                                     float* translations) {
+    if (!m || n_tmpl < 0 || batch_size < 0) return fail(FDCM_ERR_INVALID, "bad argument");
+    if (n_tmpl == 0) return FDCM_OK;
+    if (!tmpl_offsets || !alignments || !has_value || !scores || !translations) return fail(FDCM_ERR_INVALID, "null argument");
+    if (m->dm.D == 0) return fail(FDCM_ERR_INVALID, "optimize on an empty feature map");
+    if (m->stage != 0) return fail(FDCM_ERR_INVALID, "feature map was built with a debug stage");
+    const int64_t n_lines = tmpl_offsets[n_tmpl];
+    if (n_lines > 0 && !tmpl_lines) return fail(FDCM_ERR_INVALID, "tmpl_lines is null");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    int max_lines = 1;
+    for (int t = 0; t < n_tmpl; ++t) max_lines = std::max(max_lines, tmpl_offsets[t + 1] - tmpl_offsets[t]);
+    DevBuf dl, doff, dal, drec, dval, dcnt;
+    auto cleanup = [&]() { for (DevBuf* b : {&dl, &doff, &dal, &drec, &dval, &dcnt}) b->release(); };
+    std::vector<fdcm_match> rec((size_t)n_tmpl);
+    cudaError_t e = dl.reserve(std::max<size_t>(16, (size_t)n_lines * 16));
+    if (e == cudaSuccess) e = doff.reserve((size_t)(n_tmpl + 1) * 4);
+    if (e == cudaSuccess) e = dal.reserve((size_t)n_tmpl * 8);
+    if (e == cudaSuccess) e = drec.reserve((size_t)n_tmpl * sizeof(fdcm_match));
+    if (e == cudaSuccess) e = dval.reserve((size_t)n_tmpl);
+    if (e == cudaSuccess) e = dcnt.reserve(3 * 8);
+    if (e == cudaSuccess && n_lines) e = cudaMemcpyAsync(dl.p, tmpl_lines, (size_t)n_lines * 16, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(doff.p, tmpl_offsets, (size_t)(n_tmpl + 1) * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dal.p, alignments, (size_t)n_tmpl * 8, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dcnt.p, 0, 3 * 8, s);
+    if (e == cudaSuccess) {
+        TemplatesView tv{};
+        tv.lines = dl.as<float4>();
+        tv.offsets = doff.as<int32_t>();
+        tv.n_tmpl = n_tmpl;
+        tv.max_lines = max_lines;
+        SceneView sv{};
+        SearchLaunch sl{};
+        sl.batch = batch_size > 0 ? batch_size : 1;
+        sl.n_hyp = n_tmpl;
+        sl.direct_align = dal.as<float2>();
+        SearchOutputs so{};
+        so.rec = drec.as<fdcm_match>();
+        so.valid = dval.as<uint8_t>();
+        so.counters = dcnt.as<unsigned long long>();
+        KernelScope k("optimize", 0.0, s);
+        launch_search(map_view(m), m->table_dev, tv, sv, sl, so, s);
+    }
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rec.data(), drec.p, (size_t)n_tmpl * sizeof(fdcm_match), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(has_value, dval.p, (size_t)n_tmpl, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    prof_resolve();
+    cleanup();
+    if (e != cudaSuccess) return fail(FDCM_ERR_CUDA, std::string("optimize: ") + cudaGetErrorString(e));
+    for (int t = 0; t < n_tmpl; ++t) {
+        if (has_value[t]) {
+            scores[t] = rec[(size_t)t].score;
+            translations[2 * t] = rec[(size_t)t].transform[2];       // identity transform + translation
+            translations[2 * t + 1] = rec[(size_t)t].transform[5];
+        } else {
+            scores[t] = 0.f;
+            translations[2 * t] = translations[2 * t + 1] = 0.f;
+        }
+    }
+    return FDCM_OK;
 }
 
 extern "C" fdcm_status fdcm_search_host(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,

@@ -46,6 +46,8 @@ struct SearchLaunch {
     int32_t tmpl_idx_base;
     const int64_t* hyp_off;      // n_tmpl + 1 prefix of hypothesis counts
     int64_t n_hyp;
+    const float2* direct_align;  // optimize() entry point: hypothesis h = template h as given (identity transform)
+                                 // with alignment vector direct_align[h]; nullptr for the fused search
 };
 
 struct SearchOutputs {

@@ -310,40 +310,51 @@ __global__ void __launch_bounds__(128) search8_kernel(const __grid_constant__ Ma
     bool valid = false;
 
     if (active) {
-        // ---- hypothesis index -> (template, template-line rank, scene window slot, reversed) ----
-        int lo = 0, hi = tv.n_tmpl;   // largest t with hyp_off[t] <= h
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (sl.hyp_off[mid] <= h) lo = mid; else hi = mid;
-        }
-        const int t = lo;
-        const int loc = (int)(h - sl.hyp_off[t]);
-        const int l0 = tv.offsets[t];
-        const int L = tv.offsets[t + 1] - l0;
-        const int nS = min(sv.n, sl.max_scene_lines);
-        const int rank = loc / (2 * nS);
-        const int slot = (loc >> 1) % nS;
-        const int rev = loc & 1;
-        const int tline = tv.argsort[l0 + rank];
-        const float value = tv.line_len[l0 + tline];      // binarySearch with std::greater (core/math.h:138-146)
-        int b0 = 0, b1 = sv.n;
-        while (b0 < b1) {
-            const int mid = (b0 + b1) >> 1;
-            if (sv.sorted_len[mid] > value) b0 = mid + 1; else b1 = mid;
-        }
-        int closest;
-        if (b0 == 0) closest = 0;
-        else if (b0 == sv.n) closest = sv.n - 1;
-        else closest = fabsf(value - sv.sorted_len[b0]) < fabsf(value - sv.sorted_len[b0 - 1]) ? b0 : b0 - 1;
-        int rb = max(0, closest - sl.max_scene_lines / 2);   // getCenteredRange (defaultsearch.h:40-47)
-        const int re = min(rb + sl.max_scene_lines, sv.n);
-        rb = max(0, re - sl.max_scene_lines);
-        const int sline = sv.sorted_idx[rb + slot];
-        if (k == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, tline, sline, rev);
-
-        const float4* TL = tv.lines + l0;
+        int t, l0, L;
         float avx, avy;
-        const Rigid T = align_dev(TL[tline], sv.lines[sline], rev, avx, avy);   // defaultmatch.cpp:57-69
+        Rigid T;
+        if (sl.direct_align) {
+            // optimize<BatchOptimize>(templates, alignments, featuremap) (batchoptimize.cpp:6-123): template h as given
+            t = (int)h;
+            l0 = tv.offsets[t];
+            L = tv.offsets[t + 1] - l0;
+            T = Rigid{1.f, 0.f, 0.f, 0.f, 1.f, 0.f};      // x*1 + y*0 + 0 is exact: coordinates pass through unchanged
+            avx = sl.direct_align[h].x;
+            avy = sl.direct_align[h].y;
+        } else {
+            // ---- hypothesis index -> (template, template-line rank, scene window slot, reversed) ----
+            int lo = 0, hi = tv.n_tmpl;   // largest t with hyp_off[t] <= h
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (sl.hyp_off[mid] <= h) lo = mid; else hi = mid;
+            }
+            t = lo;
+            const int loc = (int)(h - sl.hyp_off[t]);
+            l0 = tv.offsets[t];
+            L = tv.offsets[t + 1] - l0;
+            const int nS = min(sv.n, sl.max_scene_lines);
+            const int rank = loc / (2 * nS);
+            const int slot = (loc >> 1) % nS;
+            const int rev = loc & 1;
+            const int tline = tv.argsort[l0 + rank];
+            const float value = tv.line_len[l0 + tline];      // binarySearch with std::greater (core/math.h:138-146)
+            int b0 = 0, b1 = sv.n;
+            while (b0 < b1) {
+                const int mid = (b0 + b1) >> 1;
+                if (sv.sorted_len[mid] > value) b0 = mid + 1; else b1 = mid;
+            }
+            int closest;
+            if (b0 == 0) closest = 0;
+            else if (b0 == sv.n) closest = sv.n - 1;
+            else closest = fabsf(value - sv.sorted_len[b0]) < fabsf(value - sv.sorted_len[b0 - 1]) ? b0 : b0 - 1;
+            int rb = max(0, closest - sl.max_scene_lines / 2);   // getCenteredRange (defaultsearch.h:40-47)
+            const int re = min(rb + sl.max_scene_lines, sv.n);
+            rb = max(0, re - sl.max_scene_lines);
+            const int sline = sv.sorted_idx[rb + slot];
+            if (k == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, tline, sline, rev);
+            T = align_dev(tv.lines[l0 + tline], sv.lines[sline], rev, avx, avy);   // defaultmatch.cpp:57-69
+        }
+        const float4* TL = tv.lines + l0;
         const float asum = fabsf(avx) + fabsf(avy);
         const bool null_vec = (double)asum <= (double)FLT_EPSILON + 1e-10 * (double)asum;   // batchoptimize.cpp:20
         if (!null_vec) {
@@ -509,7 +520,7 @@ void launch_search(const MapView& map, const SlopeTableDev& table, const Templat
                    const SearchLaunch& sl, const SearchOutputs& out, cudaStream_t s) {
     if (sl.n_hyp <= 0) return;
     static const bool use_v1 = [] { const char* e = getenv("FDCM_SEARCH_V1"); return e && e[0] == '1'; }();
-    if (use_v1) {   // one hypothesis per thread (kept for A/B measurements)
+    if (use_v1 && !sl.direct_align) {   // one hypothesis per thread (kept for A/B measurements)
         int threads = 128;
         while (threads > 32 && (size_t)threads * tv.max_lines > 96 * 1024) threads >>= 1;
         const size_t smem = (size_t)threads * tv.max_lines;

@@ -120,3 +120,17 @@ def test_penalize_sort_lengths_match_oracle():
     objs = [fdcm.Match(int(r["tmpl_idx"]), float(r["score"]), r["transform"]) for r in m[:20]]
     srt = fdcm.sort_matches(fdcm.penalize(fdcm.DefaultPenalty(), objs, lengths))
     assert [o.score for o in srt] == sorted(o.score for o in srt)
+
+
+def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu():
+    """include/openfdcm_b200/openfdcm_cuda.hpp (C++ mirror of the reference's strategy API) compiles against
+    the C ABI; without a device the example must fail with an error, never fall back to a CPU path."""
+    import subprocess
+    import torch
+    exe = os.path.join(ROOT, "examples", "cpp_pipeline")
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "cpp_pipeline.cpp"), "-L" + os.path.join(ROOT, "openfdcm_b200"),
+                           "-lfdcm_b200", "-Wl,-rpath,$ORIGIN/../openfdcm_b200", "-o", exe])
+    if not torch.cuda.is_available():
+        r = subprocess.run([exe], capture_output=True, text=True)
+        assert r.returncode == 1 and "libfdcm_b200" in r.stdout

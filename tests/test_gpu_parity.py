@@ -249,3 +249,59 @@ def test_row_pass_exact_kernel_vs_literal_oracle(n):
         want = orc.dt_pass_l2_1d(f)
         assert np.array_equal(lit[i], want), f"literal kernel row {i}"
         assert np.array_equal(got[i], want), f"exact kernel row {i}: first diff at {np.flatnonzero(got[i] != want)[:5]}"
+
+
+@pytest.mark.parametrize("batch", [10, 0], ids=["BatchOptimize(10)", "DefaultOptimize"])
+@pytest.mark.parametrize("case", KATS["batch_optimize"], ids=lambda c: c["cite"][:30])
+def test_reference_optimize_kats_on_gpu(case, batch):
+    """batchoptimize.test.cpp:35-117 / defaultoptimize.test.cpp through the CUDA OptimizeStrategy entry point."""
+    tmpl = np.array(case["tmpl"], F32)
+    if case["pre_transform"] is not None:
+        tmpl = orc.transform(tmpl, case["pre_transform"])
+    fm = fdcm.build_cuda_featuremap(np.array(case["scene"], F32), fdcm.Dt3CudaParameters(case["depth"], case["coeff"], case["padding"]))
+    opt = fdcm.BatchOptimize(batch) if batch else fdcm.DefaultOptimize()
+    res = fdcm.optimize(opt, [tmpl], [case["align_vec"]], fm)[0]
+    assert (res is not None) == case["has_value"]
+    if res is None:
+        return
+    score, tr = res
+    assert np.allclose(tr, case["translation"], rtol=0, atol=1e-5)
+    if "score_exact" in case:
+        assert score == case["score_exact"]
+    else:
+        assert abs(score - case["score_rel"]) <= 1.2e-5 * abs(case["score_rel"])
+
+
+def test_optimize_entry_point_matches_oracle():
+    scene, tmpls = _workload(91, n_tmpl=12, n_lines=27)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    rng = np.random.default_rng(4)
+    placed = [(t.T.reshape(-1, 2) + rng.uniform([200, 150], [440, 330]).astype(F32)).reshape(-1, 4).T.astype(F32) for t in tmpls]
+    placed.append((tmpls[0] * 100).astype(F32))                      # out of the map -> nullopt
+    aligns = [rng.standard_normal(2).astype(F32) for _ in placed]
+    aligns[3] = np.zeros(2, F32)                                     # null alignment vector -> nullopt
+    aligns[4] = np.array([0, 1], F32)
+    aligns[5] = np.array([-1, 0], F32)
+    for batch in (10, 3, 0):
+        opt = fdcm.BatchOptimize(batch) if batch else fdcm.DefaultOptimize()
+        got = fdcm.optimize(opt, placed, aligns, g)
+        for t, a, r in zip(placed, aligns, got):
+            has, score, tr = c.optimize_one(t, a, batch)
+            assert (r is not None) == has
+            if has:
+                assert r[0] == score and np.array_equal(r[1], tr)
+
+
+def test_cpp_host_mirror_pipeline():
+    """examples/cpp_pipeline.cpp: README flow through include/openfdcm_b200/openfdcm_cuda.hpp."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "examples", "cpp_pipeline")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-I" + os.path.join(root, "include"), os.path.join(root, "examples", "cpp_pipeline.cpp"),
+                               "-L" + os.path.join(root, "openfdcm_b200"), "-lfdcm_b200", "-Wl,-rpath,$ORIGIN/../openfdcm_b200", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "matches; best" in r.stdout
