@@ -354,32 +354,104 @@ __device__ __forceinline__ int lane_owner(const uint32_t* f, const uint32_t* bmi
     return arg;
 }
 
+// leftmost argmin of f[v] + (q-v)^2 over v in [lo, hi], all 32 lanes cooperating (uniform arguments).
+// Blocks whose lower bound bmin + dist(q, block)^2 exceeds the best known cost are skipped.
+__device__ int coop_owner(const uint32_t* f, const uint32_t* bmin, const uint16_t* bpos, int q, int lo, int hi, int lane) {
+    unsigned long long best = ~0ull;
+    if (hi - lo < 96) {
+        for (int v = lo + lane; v <= hi; v += 32) {
+            const int d = q - v;
+            const unsigned long long key = ((unsigned long long)(f[v] + (uint32_t)(d * d)) << 16) | (unsigned)v;
+            best = key < best ? key : best;
+        }
+    } else {
+        const int b_lo = lo >> 5, b_hi = hi >> 5;
+        int d = q - lo;
+        uint32_t U = f[lo] + (uint32_t)(d * d);
+        d = q - hi;
+        U = min(U, f[hi] + (uint32_t)(d * d));
+        for (int b = b_lo + 1 + lane; b < b_hi; b += 32) {   // interior blocks: their minima are valid candidates
+            d = q - (int)bpos[b];
+            U = min(U, bmin[b] + (uint32_t)(d * d));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) U = min(U, __shfl_xor_sync(0xffffffffu, U, o));
+        for (int b0 = b_lo; b0 <= b_hi; b0 += 32) {
+            const int b = b0 + lane;
+            bool surv = false;
+            if (b <= b_hi) {
+                const int v0 = max(b << 5, lo), v1 = min((b << 5) + 31, hi);
+                const int dist = q < v0 ? v0 - q : (q > v1 ? q - v1 : 0);
+                surv = bmin[b] + (uint32_t)(dist * dist) <= U;   // ties must be scanned (leftmost argmin)
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, surv);
+            while (todo) {
+                const int v = ((b0 + __ffs(todo) - 1) << 5) + lane;
+                todo &= todo - 1;
+                if (v >= lo && v <= hi) {
+                    d = q - v;
+                    const unsigned long long key = ((unsigned long long)(f[v] + (uint32_t)(d * d)) << 16) | (unsigned)v;
+                    best = key < best ? key : best;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+        best = other < best ? other : best;
+    }
+    return (int)(best & 0xFFFFu);
+}
+
+// leftmost argmin over a short bracket by one lane
+__device__ __forceinline__ int scan_owner(const uint32_t* f, int q, int lo, int hi) {
+    int d = q - lo;
+    uint32_t best = f[lo] + (uint32_t)(d * d);
+    int arg = lo;
+    for (int v = lo + 1; v <= hi; ++v) {
+        d = q - v;
+        const uint32_t c = f[v] + (uint32_t)(d * d);
+        if (c < best) { best = c; arg = v; }
+    }
+    return arg;
+}
+
+constexpr int kQueueCap = 1024;   // intervals in flight per row (power of two)
+constexpr uint16_t kUnknown = 0xFFFFu;
+
+// Interval refinement.  pt[q] holds the owner of q at "known" pixels (0xFFFF elsewhere).  An interval (a, b) of known
+// pixels with owners oa != ob is split at the crossing x* of the two parabolas oa, ob (the last pixel where oa is
+// not worse): because every other parabola minus that two-parabola envelope is convex piecewise linear with its
+// minimum at the crossing, a third owner can exist inside (a, b) only if it already wins at x* or x*+1.  So the
+// owners of x* and x*+1 (searched over [oa, ob] only, owners are monotone) either certify the boundary or split
+// the interval further.  Work is proportional to the number of owner runs, not to the row length.
 __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
                                                            MapDims dm, int n_rows_total) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warps = blockDim.x >> 5;
     const int n = dm.W;
-    // per warp: f[pitch] u32 | bmin[96] u32 | owner[pitch] u16 | bpos[96] u16
-    const size_t per_warp = (size_t)dm.pitch * 6 + kMaxBlocks * 6;
+    // per warp: f[pitch] u32 | bmin[96] u32 | queue[kQueueCap] u32 | pt[pitch] u16 | bpos[96] u16
+    const size_t per_warp = (size_t)dm.pitch * 6 + kMaxBlocks * 6 + kQueueCap * 4;
     unsigned char* base = smem_raw + (size_t)warp * per_warp;
     uint32_t* f = reinterpret_cast<uint32_t*>(base);
     uint32_t* bmin = f + dm.pitch;
-    uint16_t* owner = reinterpret_cast<uint16_t*>(bmin + kMaxBlocks);
-    uint16_t* bpos = owner + dm.pitch;
-    (void)warps;
+    uint32_t* queue = bmin + kMaxBlocks;
+    uint16_t* pt = reinterpret_cast<uint16_t*>(queue + kQueueCap);
+    uint16_t* bpos = pt + dm.pitch;
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // row of the [D*H][pitch] stack of planes
     if (row >= n_rows_total) return;
     const uint16_t* gin = g + (size_t)row * dm.pitch;
     float* out = planes + (size_t)row * dm.pitch;
 
-    // ---- load g, f = g^2; first / last finite column ----
+    // ---- load g, f = g^2; first / last finite column; clear pt ----
     int cmin = 0x7fffffff, cmax = -1;
     for (int x = lane * 2; x < dm.pitch; x += 64) {
         const uint32_t two = *reinterpret_cast<const uint32_t*>(gin + x);
         const uint32_t g0 = (x < n) ? (two & 0xFFFFu) : kNoEdge16, g1 = (x + 1 < n) ? (two >> 16) : kNoEdge16;
         f[x] = g0 == kNoEdge16 ? kBigF : g0 * g0;
         f[x + 1] = g1 == kNoEdge16 ? kBigF : g1 * g1;
+        *reinterpret_cast<uint32_t*>(pt + x) = 0xFFFFFFFFu;
         if (g0 != kNoEdge16) { cmin = min(cmin, x); cmax = max(cmax, x); }
         if (g1 != kNoEdge16) { cmin = min(cmin, x + 1); cmax = max(cmax, x + 1); }
     }
@@ -408,25 +480,105 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
     }
     __syncwarp();
 
-    // ---- owners by divide and conquer ----
-    // level A: every 32nd pixel (q = 31, 63, ...) searched over the whole finite range [cmin, cmax]
-    for (int q = 31 + 32 * lane; q < n; q += 1024) owner[q] = (uint16_t)lane_owner(f, bmin, bpos, q, cmin, cmax);
-    __syncwarp();
-    // levels s = 16 .. 1: q+1 = s * odd, bracketed by the owners of q-s and q+s
-    for (int s = 16; s >= 1; s >>= 1) {
-        for (int q = s - 1 + 2 * s * lane; q < n; q += 64 * s) {
-            const int lo = (q - s >= 0) ? owner[q - s] : cmin;
-            const int hi = (q + s < n) ? owner[q + s] : cmax;
-            owner[q] = (uint16_t)((lo == hi) ? lo : lane_owner(f, bmin, bpos, q, lo, hi));
+    // ---- owners of the two end pixels, then breadth-first interval refinement ----
+    bool overflow = false;
+    {
+        const int o0 = coop_owner(f, bmin, bpos, 0, cmin, cmax, lane);
+        const int o1 = (n > 1) ? coop_owner(f, bmin, bpos, n - 1, o0, cmax, lane) : o0;
+        if (lane == 0) {
+            pt[0] = (uint16_t)o0;
+            pt[n - 1] = (uint16_t)o1;
+            queue[0] = (uint32_t)(n - 1) << 16;   // interval (a = 0, b = n-1): a in the low half, b in the high half
         }
+    }
+    __syncwarp();
+    unsigned head = 0, tail = (n > 1) ? 1u : 0u;   // uniform across the warp
+    while (head != tail) {
+        const unsigned cnt = min(32u, tail - head);
+        const bool act = (unsigned)lane < cnt;
+        int a = 0, b = 0, oa = 0, ob = 0;
+        if (act) {
+            const uint32_t e = queue[(head + lane) & (kQueueCap - 1)];
+            a = (int)(e & 0xFFFFu);
+            b = (int)(e >> 16);
+            oa = pt[a];
+            ob = pt[b];
+        }
+        head += cnt;
+        // an interval needs work only if its end owners differ and it has interior pixels
+        const bool work = act && oa != ob && b > a + 1;
+        int x = 0, w1 = 0, w2 = 0;
+        bool is_long = false;
+        if (work) {
+            // last pixel where parabola oa is not worse than ob: floor((f_b - f_a + ob^2 - oa^2) / (2 (ob - oa)))
+            const int num = (int)f[ob] - (int)f[oa] + ob * ob - oa * oa;
+            const int den = 2 * (ob - oa);
+            int xs = num / den;
+            if (num % den != 0 && num < 0) --xs;
+            x = min(max(xs, a), b - 1);
+            is_long = (ob - oa) > kScanLen;
+            if (!is_long) {
+                w1 = (x == a) ? oa : scan_owner(f, x, oa, ob);
+                w2 = (x + 1 == b) ? ob : scan_owner(f, x + 1, w1, ob);
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, is_long);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int xq = __shfl_sync(0xffffffffu, x, src);
+            const int la = __shfl_sync(0xffffffffu, a, src), lb = __shfl_sync(0xffffffffu, b, src);
+            const int l2 = __shfl_sync(0xffffffffu, oa, src), h2 = __shfl_sync(0xffffffffu, ob, src);
+            const int r1 = (xq == la) ? l2 : coop_owner(f, bmin, bpos, xq, l2, h2, lane);
+            const int r2 = (xq + 1 == lb) ? h2 : ((r1 == h2) ? h2 : coop_owner(f, bmin, bpos, xq + 1, r1, h2, lane));
+            if (lane == src) { w1 = r1; w2 = r2; }
+        }
+        // publish the two new known pixels and enqueue the children that still straddle a boundary
+        bool c1 = false, c2 = false;
+        if (work) {
+            pt[x] = (uint16_t)w1;
+            pt[x + 1] = (uint16_t)w2;
+            c1 = (w1 != oa) && (x > a + 1);
+            c2 = (w2 != ob) && (b > x + 2);
+        }
+        const unsigned m1 = __ballot_sync(0xffffffffu, c1), m2 = __ballot_sync(0xffffffffu, c2);
+        const unsigned n1 = __popc(m1), n2 = __popc(m2);
+        if (tail - head + n1 + n2 > (unsigned)kQueueCap) { overflow = true; break; }
+        const unsigned lt = (1u << lane) - 1u;
+        if (c1) queue[(tail + __popc(m1 & lt)) & (kQueueCap - 1)] = (uint32_t)a | ((uint32_t)x << 16);
+        if (c2) queue[(tail + n1 + __popc(m2 & lt)) & (kQueueCap - 1)] = (uint32_t)(x + 1) | ((uint32_t)b << 16);
+        tail += n1 + n2;
         __syncwarp();
     }
+    if (overflow) {
+        // more than kQueueCap open intervals (very dense rows): plain divide and conquer over every pixel
+        __syncwarp();
+        for (int q = 31 + 32 * lane; q < n; q += 1024) pt[q] = (uint16_t)lane_owner(f, bmin, bpos, q, cmin, cmax);
+        __syncwarp();
+        for (int s = 16; s >= 1; s >>= 1) {
+            for (int q = s - 1 + 2 * s * lane; q < n; q += 64 * s) {
+                const int lo = (q - s >= 0) ? pt[q - s] : cmin;
+                const int hi = (q + s < n) ? pt[q + s] : cmax;
+                pt[q] = (uint16_t)((lo == hi) ? lo : lane_owner(f, bmin, bpos, q, lo, hi));
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
 
     // ---- chained values, in place, 32 pixels at a time (imgproc.h:122-128 incl. its aliasing) ----
+    int carry = 0;   // owner of the last known pixel of the previous chunks (pixel 0 is always known)
     for (int x0 = 0; x0 < n; x0 += 32) {
         const int q = x0 + lane;
         const bool act = q < n;
-        const int u = act ? owner[q] : 0;
+        // owner(q) = owner of the nearest known pixel at or left of q
+        const unsigned pv = act ? pt[q] : kUnknown;
+        const unsigned known = __ballot_sync(0xffffffffu, pv != kUnknown);
+        const unsigned le = known & (0xFFFFFFFFu >> (31 - lane));
+        const int srcl = le ? 31 - __clz(le) : 0;
+        const int ul = __shfl_sync(0xffffffffu, (int)pv, srcl);
+        const int u = le ? ul : carry;
+        if (known) carry = __shfl_sync(0xffffffffu, (int)pv, 31 - __clz(known));
         const int d = q - u;
         const uint32_t add = (uint32_t)(d * d);
         uint32_t val = 0;
@@ -710,8 +862,8 @@ void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, f
 }
 
 void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {
-    const int warps = 4;
-    const size_t smem = (size_t)warps * ((size_t)dm.pitch * 6 + 96 * 6);
+    const int warps = 2;
+    const size_t smem = (size_t)warps * ((size_t)dm.pitch * 6 + 96 * 6 + 1024 * 4);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(dt_row_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
