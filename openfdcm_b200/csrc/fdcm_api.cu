@@ -203,7 +203,8 @@ struct fdcm_dt3 {
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
     mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
-        s_topk_out, s_topk_n;
+        s_topk_out, s_topk_n, s_keys, s_keys2, s_idx, s_perm, s_sort_tmp;
+    mutable float s_scene_min[2] = {0.f, 0.f}, s_scene_max[2] = {0.f, 0.f};   // bbox of the resident search scene
     mutable int32_t s_scene_n = 0;      // scene lines currently resident for the search (original, un-shifted)
     mutable int64_t last_n_hyp = 0;
     mutable fdcm_search_stats last_stats{};
@@ -213,7 +214,8 @@ struct fdcm_dt3 {
     ~fdcm_dt3() {
         cudaSetDevice(device);
         for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &rtab, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
-                          &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n})
+                          &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n, &s_keys, &s_keys2, &s_idx,
+                          &s_perm, &s_sort_tmp})
             b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
     }
@@ -231,6 +233,14 @@ static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, in
         sorted_idx[(size_t)i] = (int32_t)sidx[(size_t)i];
     }
     m->s_scene_n = 0;
+    m->s_scene_min[0] = m->s_scene_max[0] = scene[0];
+    m->s_scene_min[1] = m->s_scene_max[1] = scene[1];
+    for (int64_t i = 0; i < 2 * (int64_t)n_scene; ++i)
+        for (int a = 0; a < 2; ++a) {
+            const float v = scene[2 * i + a];
+            if (v < m->s_scene_min[a]) m->s_scene_min[a] = v;
+            if (v > m->s_scene_max[a]) m->s_scene_max[a] = v;
+        }
     CUDA_TRY(m->s_scene.reserve((size_t)n_scene * 16));
     CUDA_TRY(m->s_sorted_len.reserve((size_t)n_scene * 4));
     CUDA_TRY(m->s_sorted_idx.reserve((size_t)n_scene * 4));
@@ -812,6 +822,26 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     so.valid = m->s_valid.as<uint8_t>();
     so.hyp = m->s_hyp.as<int4>();
     so.counters = m->s_counters.as<unsigned long long>();
+    sl.perm = nullptr;
+    static const bool no_order = [] { const char* e = std::getenv("FDCM_SEARCH_UNORDERED"); return e && e[0] == '1'; }();
+    if (!no_order && H >= 4096 && H < (int64_t)1 << 31) {
+        // process the hypotheses in the spatial order of their scene lines (L2 locality of the map gathers)
+        const float ex = m->s_scene_max[0] - m->s_scene_min[0], ey = m->s_scene_max[1] - m->s_scene_min[1];
+        const int cells_x = std::min(4096, std::max(1, (int)(ex / 128.f) + 1));
+        const int cells_y = std::min(4096, std::max(1, (int)(ey / 128.f) + 1));
+        int key_bits = 1;
+        while (((int64_t)1 << key_bits) < (int64_t)cells_x * cells_y) ++key_bits;
+        const size_t tmp = search_order_temp_bytes(H);
+        CUDA_TRY(m->s_keys.reserve((size_t)H * 4));
+        CUDA_TRY(m->s_keys2.reserve((size_t)H * 4));
+        CUDA_TRY(m->s_idx.reserve((size_t)H * 4));
+        CUDA_TRY(m->s_perm.reserve((size_t)H * 4));
+        CUDA_TRY(m->s_sort_tmp.reserve(std::max<size_t>(tmp, 16)));
+        KernelScope k("search_order", 0.0, s, 4);
+        launch_search_order(tv, sv, sl, m->s_keys.as<uint32_t>(), m->s_keys2.as<uint32_t>(), m->s_idx.as<int32_t>(),
+                            m->s_perm.as<int32_t>(), m->s_sort_tmp.p, tmp, m->s_scene_min[0], m->s_scene_min[1], cells_x, key_bits, s);
+        sl.perm = m->s_perm.as<int32_t>();
+    }
     {
         KernelScope k("search", 0.0, s);
         launch_search(map_view(m), m->table_dev, tv, sv, sl, so, s);
@@ -915,6 +945,7 @@ extern "C" fdcm_status fdcm_optimize(const fdcm_dt3* m, const float* tmpl_lines,
         SearchLaunch sl{};
         sl.batch = batch_size > 0 ? batch_size : 1;
         sl.n_hyp = n_tmpl;
+        sl.perm = nullptr;
         sl.direct_align = dal.as<float2>();
         SearchOutputs so{};
         so.rec = drec.as<fdcm_match>();

@@ -12,6 +12,8 @@
 #include <climits>
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -280,6 +282,73 @@ __global__ void __launch_bounds__(128) search_kernel(const __grid_constant__ Map
     }
 }
 
+// hypothesis index -> (template, template line, scene line, reversed): establishSearchStrategy<DefaultSearch>
+// (defaultsearch.cpp:29-49) evaluated for one combination
+struct HypDecode { int t, l0, L, tline, sline, rev; };
+__device__ __forceinline__ HypDecode decode_hypothesis(long long h, const TemplatesView& tv, const SceneView& sv, const SearchLaunch& sl) {
+    HypDecode r;
+    int lo = 0, hi = tv.n_tmpl;   // largest t with hyp_off[t] <= h
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (sl.hyp_off[mid] <= h) lo = mid; else hi = mid;
+    }
+    r.t = lo;
+    const int loc = (int)(h - sl.hyp_off[r.t]);
+    r.l0 = tv.offsets[r.t];
+    r.L = tv.offsets[r.t + 1] - r.l0;
+    const int nS = min(sv.n, sl.max_scene_lines);
+    const int rank = loc / (2 * nS);
+    const int slot = (loc >> 1) % nS;
+    r.rev = loc & 1;
+    r.tline = tv.argsort[r.l0 + rank];
+    const float value = tv.line_len[r.l0 + r.tline];      // binarySearch with std::greater (core/math.h:138-146)
+    int b0 = 0, b1 = sv.n;
+    while (b0 < b1) {
+        const int mid = (b0 + b1) >> 1;
+        if (sv.sorted_len[mid] > value) b0 = mid + 1; else b1 = mid;
+    }
+    int closest;
+    if (b0 == 0) closest = 0;
+    else if (b0 == sv.n) closest = sv.n - 1;
+    else closest = fabsf(value - sv.sorted_len[b0]) < fabsf(value - sv.sorted_len[b0 - 1]) ? b0 : b0 - 1;
+    int rb = max(0, closest - sl.max_scene_lines / 2);   // getCenteredRange (defaultsearch.h:40-47)
+    const int re = min(rb + sl.max_scene_lines, sv.n);
+    rb = max(0, re - sl.max_scene_lines);
+    r.sline = sv.sorted_idx[rb + slot];
+    return r;
+}
+
+// Spatial sort key of a hypothesis: the 128-pixel cell (row-major) of the centre of its scene line.  All
+// hypotheses aligned on nearby scene lines gather from the same neighbourhood of the map, so processing them
+// together keeps that neighbourhood (all D planes) resident in L2.  The order only affects scheduling; results
+// are written at the hypothesis index.
+__global__ void search_key_kernel(const __grid_constant__ TemplatesView tv, const __grid_constant__ SceneView sv,
+                                  const __grid_constant__ SearchLaunch sl, float minx, float miny, int cells_x,
+                                  uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
+    const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= sl.n_hyp) return;
+    const HypDecode d = decode_hypothesis(h, tv, sv, sl);
+    const float4 s = sv.lines[d.sline];
+    const int cx = min(max((int)(((s.x + s.z) * 0.5f - minx) * (1.f / 128.f)), 0), cells_x - 1);
+    const int cy = min(max((int)(((s.y + s.w) * 0.5f - miny) * (1.f / 128.f)), 0), 4095);
+    keys[h] = (uint32_t)(cy * cells_x + cx);
+    idx[h] = (int32_t)h;
+}
+
+size_t search_order_temp_bytes(int64_t n_hyp) {
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const int32_t*)nullptr,
+                                    (int32_t*)nullptr, (int)n_hyp);
+    return bytes;
+}
+
+void launch_search_order(const TemplatesView& tv, const SceneView& sv, const SearchLaunch& sl, uint32_t* d_keys, uint32_t* d_keys_out,
+                         int32_t* d_idx, int32_t* d_perm, void* d_temp, size_t temp_bytes, float minx, float miny, int cells_x,
+                         int key_bits, cudaStream_t s) {
+    search_key_kernel<<<(unsigned)((sl.n_hyp + 255) / 256), 256, 0, s>>>(tv, sv, sl, minx, miny, cells_x, d_keys, d_idx);
+    cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_out, d_idx, d_perm, (int)sl.n_hyp, 0, key_bits, s);
+}
+
 // =============================================================================================
 // K5+K6, cooperative version: 8 lanes per hypothesis.  Eigen's packet-4, 2x-unrolled reduction keeps 8
 // partial sums (A0..A3, B0..B3) where partial k accumulates lines k, k+8, k+16, ... in order; lane k of a
@@ -304,8 +373,9 @@ __global__ void __launch_bounds__(128) search8_kernel(const __grid_constant__ Ma
     const unsigned gmask = 0xFFu << gbase;
     const int hyps_per_block = blockDim.x / kGroup;
     const int hb = tid / kGroup;                         // hypothesis slot in the block
-    const long long h = (long long)blockIdx.x * hyps_per_block + hb;
-    const bool active = h < sl.n_hyp;
+    const long long slot_idx = (long long)blockIdx.x * hyps_per_block + hb;
+    const bool active = slot_idx < sl.n_hyp;
+    const long long h = active ? (sl.perm ? (long long)sl.perm[slot_idx] : slot_idx) : 0;
     unsigned long long n_eval = 0, n_look = 0;
     bool valid = false;
 
@@ -322,37 +392,10 @@ __global__ void __launch_bounds__(128) search8_kernel(const __grid_constant__ Ma
             avx = sl.direct_align[h].x;
             avy = sl.direct_align[h].y;
         } else {
-            // ---- hypothesis index -> (template, template-line rank, scene window slot, reversed) ----
-            int lo = 0, hi = tv.n_tmpl;   // largest t with hyp_off[t] <= h
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (sl.hyp_off[mid] <= h) lo = mid; else hi = mid;
-            }
-            t = lo;
-            const int loc = (int)(h - sl.hyp_off[t]);
-            l0 = tv.offsets[t];
-            L = tv.offsets[t + 1] - l0;
-            const int nS = min(sv.n, sl.max_scene_lines);
-            const int rank = loc / (2 * nS);
-            const int slot = (loc >> 1) % nS;
-            const int rev = loc & 1;
-            const int tline = tv.argsort[l0 + rank];
-            const float value = tv.line_len[l0 + tline];      // binarySearch with std::greater (core/math.h:138-146)
-            int b0 = 0, b1 = sv.n;
-            while (b0 < b1) {
-                const int mid = (b0 + b1) >> 1;
-                if (sv.sorted_len[mid] > value) b0 = mid + 1; else b1 = mid;
-            }
-            int closest;
-            if (b0 == 0) closest = 0;
-            else if (b0 == sv.n) closest = sv.n - 1;
-            else closest = fabsf(value - sv.sorted_len[b0]) < fabsf(value - sv.sorted_len[b0 - 1]) ? b0 : b0 - 1;
-            int rb = max(0, closest - sl.max_scene_lines / 2);   // getCenteredRange (defaultsearch.h:40-47)
-            const int re = min(rb + sl.max_scene_lines, sv.n);
-            rb = max(0, re - sl.max_scene_lines);
-            const int sline = sv.sorted_idx[rb + slot];
-            if (k == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, tline, sline, rev);
-            T = align_dev(tv.lines[l0 + tline], sv.lines[sline], rev, avx, avy);   // defaultmatch.cpp:57-69
+            const HypDecode d = decode_hypothesis(h, tv, sv, sl);
+            t = d.t; l0 = d.l0; L = d.L;
+            if (k == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);
+            T = align_dev(tv.lines[l0 + d.tline], sv.lines[d.sline], d.rev, avx, avy);   // defaultmatch.cpp:57-69
         }
         const float4* TL = tv.lines + l0;
         const float asum = fabsf(avx) + fabsf(avy);

@@ -305,3 +305,19 @@ def test_cpp_host_mirror_pipeline():
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "matches; best" in r.stdout
+
+
+def test_search_spatially_ordered_path():
+    """>= 4096 hypotheses: the kernel walks the hypotheses in the spatial order of their scene lines; the match list
+    must still come back in hypothesis order, bit-identical to the oracle."""
+    scene, tmpls = _workload(123, n_tmpl=150, n_lines=20)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    got = fdcm.search_all(g, tmpls, scene, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5))
+    raw, hyp = c.search(tmpls, scene, 4, 4, batch=10, want_hyp=True)
+    want = orc.penalize(1, 1.5, raw, orc.template_lengths(tmpls))
+    assert len(hyp) == 150 * 32 and np.array_equal(g.last_hypotheses(), hyp)
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
+    top = fdcm.search_topk(g, tmpls, scene, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
+    assert np.array_equal(top, want[np.lexsort((np.arange(len(want)), want["score"]))[:10]])
