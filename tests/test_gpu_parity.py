@@ -321,3 +321,39 @@ def test_search_spatially_ordered_path():
     assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
     top = fdcm.search_topk(g, tmpls, scene, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
     assert np.array_equal(top, want[np.lexsort((np.arange(len(want)), want["score"]))[:10]])
+
+
+def test_config4_shape_wide_search_4k_scene():
+    """BASELINE config 4 shape (scaled in template count only): 4K scene, 5000 lines, 60-line templates,
+    DefaultSearch(16,16), BatchOptimize(20).  Side 5760 > 2897 -> literal DT path; 3.98 GB map."""
+    scene = synth_scene(3840, 2160, 5000, seed=4000)
+    tmpls = synth_templates(6, 60, 3840, seed=4001)
+    scene = plant_instances(scene, tmpls, 3840, 2160, seed=4002)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    assert g.width == 5760 and g.info.exact_dt_path == 0
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    for d in (0, 4, 11, 15, 22, 29):
+        assert np.array_equal(g.plane(d), c.plane(d)), f"plane {d}"
+    got = fdcm.search_all(g, tmpls, scene, fdcm.DefaultSearch(16, 16), fdcm.BatchOptimize(20))
+    want, hyp = c.search(tmpls, scene, 16, 16, batch=20, want_hyp=True)
+    assert len(hyp) == 6 * 16 * 16 * 2 and np.array_equal(g.last_hypotheses(), hyp)
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
+
+
+def test_config5_shape_multiview_batch():
+    """BASELINE config 5 shape (scaled): several scenes, one resident template set, per-scene rebuild of the same map
+    object + top-10; scene sharding helper assigns scenes to ranks."""
+    from openfdcm_b200 import distributed as fd
+    tmpls = synth_templates(30, 40, 640, seed=5100)
+    tset = fdcm.TemplateSet(tmpls)
+    scenes = [plant_instances(synth_scene(640, 480, 200, seed=5000 + s), tmpls, 640, 480, seed=5200 + s) for s in range(4)]
+    assert sorted(fd.shard_scenes(4, 0, 2) + fd.shard_scenes(4, 1, 2)) == [0, 1, 2, 3]
+    fm = fdcm.build_cuda_featuremap(scenes[0], fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    for s, scene in enumerate(scenes):
+        if s:
+            fm.rebuild(scene)
+        top = fdcm.search_topk(fm, tset, None, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
+        c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+        pen = orc.penalize(1, 1.5, c.search(tmpls, scene, 4, 4, batch=10), orc.template_lengths(tmpls))
+        assert np.array_equal(top, pen[np.lexsort((np.arange(len(pen)), pen["score"]))[:10]]), f"scene {s}"
