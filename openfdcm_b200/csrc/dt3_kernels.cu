@@ -404,6 +404,68 @@ __device__ int coop_owner(const uint32_t* f, const uint32_t* bmin, const uint16_
     return (int)(best & 0xFFFFu);
 }
 
+// owners of q and q+1 over [lo, hi] in one cooperative pass (shared loads and block pruning);
+// (q+1-v)^2 = (q-v)^2 + 2(q-v) + 1
+__device__ void coop_owner_pair(const uint32_t* f, const uint32_t* bmin, const uint16_t* bpos, int q, int lo, int hi, int lane,
+                                int& w1, int& w2) {
+    unsigned long long best1 = ~0ull, best2 = ~0ull;
+    auto eval = [&](int v) {
+        const int d = q - v;
+        const uint32_t c1 = f[v] + (uint32_t)(d * d);
+        const uint32_t c2 = (uint32_t)((int)c1 + 2 * d + 1);
+        const unsigned long long k1 = ((unsigned long long)c1 << 16) | (unsigned)v, k2 = ((unsigned long long)c2 << 16) | (unsigned)v;
+        best1 = k1 < best1 ? k1 : best1;
+        best2 = k2 < best2 ? k2 : best2;
+    };
+    if (hi - lo < 96) {
+        for (int v = lo + lane; v <= hi; v += 32) eval(v);
+    } else {
+        const int b_lo = lo >> 5, b_hi = hi >> 5;
+        int d = q - lo;
+        uint32_t c = f[lo] + (uint32_t)(d * d);
+        uint32_t U1 = c, U2 = (uint32_t)((int)c + 2 * d + 1);
+        d = q - hi;
+        c = f[hi] + (uint32_t)(d * d);
+        U1 = min(U1, c);
+        U2 = min(U2, (uint32_t)((int)c + 2 * d + 1));
+        for (int b = b_lo + 1 + lane; b < b_hi; b += 32) {
+            d = q - (int)bpos[b];
+            c = bmin[b] + (uint32_t)(d * d);
+            U1 = min(U1, c);
+            U2 = min(U2, (uint32_t)((int)c + 2 * d + 1));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            U1 = min(U1, __shfl_xor_sync(0xffffffffu, U1, o));
+            U2 = min(U2, __shfl_xor_sync(0xffffffffu, U2, o));
+        }
+        for (int b0 = b_lo; b0 <= b_hi; b0 += 32) {
+            const int b = b0 + lane;
+            bool surv = false;
+            if (b <= b_hi) {
+                const int v0 = max(b << 5, lo), v1 = min((b << 5) + 31, hi);
+                const int dist1 = q < v0 ? v0 - q : (q > v1 ? q - v1 : 0);
+                const int dist2 = q + 1 < v0 ? v0 - q - 1 : (q + 1 > v1 ? q + 1 - v1 : 0);
+                surv = bmin[b] + (uint32_t)(dist1 * dist1) <= U1 || bmin[b] + (uint32_t)(dist2 * dist2) <= U2;
+            }
+            unsigned todo = __ballot_sync(0xffffffffu, surv);
+            while (todo) {
+                const int v = ((b0 + __ffs(todo) - 1) << 5) + lane;
+                todo &= todo - 1;
+                if (v >= lo && v <= hi) eval(v);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, best1, o), o2 = __shfl_xor_sync(0xffffffffu, best2, o);
+        best1 = o1 < best1 ? o1 : best1;
+        best2 = o2 < best2 ? o2 : best2;
+    }
+    w1 = (int)(best1 & 0xFFFFu);
+    w2 = (int)(best2 & 0xFFFFu);
+}
+
 // leftmost argmin over a short bracket by one lane
 __device__ __forceinline__ int scan_owner(const uint32_t* f, int q, int lo, int hi) {
     int d = q - lo;
@@ -426,19 +488,23 @@ constexpr uint16_t kUnknown = 0xFFFFu;
 // minimum at the crossing, a third owner can exist inside (a, b) only if it already wins at x* or x*+1.  So the
 // owners of x* and x*+1 (searched over [oa, ob] only, owners are monotone) either certify the boundary or split
 // the interval further.  Work is proportional to the number of owner runs, not to the row length.
+// Only the columns [win_lo, win_lo + win_w) (multiples of 32; the scene's column range) can hold edges, so only they
+// need a slot in the f / out array; pixels outside are never an owner and are written straight to global memory.
 __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
-                                                           MapDims dm, int n_rows_total) {
+                                                           MapDims dm, int n_rows_total, int win_lo, int win_w) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = dm.W;
-    // per warp: f[pitch] u32 | bmin[96] u32 | queue[kQueueCap] u32 | pt[pitch] u16 | bpos[96] u16
-    const size_t per_warp = (size_t)dm.pitch * 6 + kMaxBlocks * 6 + kQueueCap * 4;
+    // per warp: fwin[win_w] u32 | bmin[96] u32 | queue[kQueueCap] u32 | pt[pitch] u16 | bpos[96] u16
+    const size_t per_warp = (size_t)win_w * 4 + (size_t)dm.pitch * 2 + kMaxBlocks * 6 + kQueueCap * 4;
     unsigned char* base = smem_raw + (size_t)warp * per_warp;
-    uint32_t* f = reinterpret_cast<uint32_t*>(base);
-    uint32_t* bmin = f + dm.pitch;
+    uint32_t* fwin = reinterpret_cast<uint32_t*>(base);
+    uint32_t* f = fwin - win_lo;                 // absolute column index; only dereferenced inside the window
+    uint32_t* bmin = fwin + win_w;
     uint32_t* queue = bmin + kMaxBlocks;
     uint16_t* pt = reinterpret_cast<uint16_t*>(queue + kQueueCap);
     uint16_t* bpos = pt + dm.pitch;
+    const int win_hi = win_lo + win_w;           // exclusive
     const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // row of the [D*H][pitch] stack of planes
     if (row >= n_rows_total) return;
     const uint16_t* gin = g + (size_t)row * dm.pitch;
@@ -446,12 +512,12 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
 
     // ---- load g, f = g^2; first / last finite column; clear pt ----
     int cmin = 0x7fffffff, cmax = -1;
-    for (int x = lane * 2; x < dm.pitch; x += 64) {
+    for (int x = lane * 2; x < dm.pitch; x += 64) *reinterpret_cast<uint32_t*>(pt + x) = 0xFFFFFFFFu;
+    for (int x = win_lo + lane * 2; x < win_hi; x += 64) {
         const uint32_t two = *reinterpret_cast<const uint32_t*>(gin + x);
         const uint32_t g0 = (x < n) ? (two & 0xFFFFu) : kNoEdge16, g1 = (x + 1 < n) ? (two >> 16) : kNoEdge16;
         f[x] = g0 == kNoEdge16 ? kBigF : g0 * g0;
         f[x + 1] = g1 == kNoEdge16 ? kBigF : g1 * g1;
-        *reinterpret_cast<uint32_t*>(pt + x) = 0xFFFFFFFFu;
         if (g0 != kNoEdge16) { cmin = min(cmin, x); cmax = max(cmax, x); }
         if (g1 != kNoEdge16) { cmin = min(cmin, x + 1); cmax = max(cmax, x + 1); }
     }
@@ -466,8 +532,7 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
     }
     __syncwarp();
     // ---- per-block minima (lane = block, rotated column order: conflict-free) ----
-    const int nb = dm.pitch >> 5;
-    for (int b = lane; b < nb; b += 32) {
+    for (int b = (win_lo >> 5) + lane; b < (win_hi >> 5); b += 32) {
         uint32_t m = 0xFFFFFFFFu;
         int pos = 0;
         for (int i = 0; i < 32; ++i) {
@@ -529,8 +594,16 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
             const int xq = __shfl_sync(0xffffffffu, x, src);
             const int la = __shfl_sync(0xffffffffu, a, src), lb = __shfl_sync(0xffffffffu, b, src);
             const int l2 = __shfl_sync(0xffffffffu, oa, src), h2 = __shfl_sync(0xffffffffu, ob, src);
-            const int r1 = (xq == la) ? l2 : coop_owner(f, bmin, bpos, xq, l2, h2, lane);
-            const int r2 = (xq + 1 == lb) ? h2 : ((r1 == h2) ? h2 : coop_owner(f, bmin, bpos, xq + 1, r1, h2, lane));
+            int r1, r2;
+            if (xq == la) {
+                r1 = l2;
+                r2 = (xq + 1 == lb) ? h2 : coop_owner(f, bmin, bpos, xq + 1, l2, h2, lane);
+            } else if (xq + 1 == lb) {
+                r2 = h2;
+                r1 = coop_owner(f, bmin, bpos, xq, l2, h2, lane);
+            } else {
+                coop_owner_pair(f, bmin, bpos, xq, l2, h2, lane, r1, r2);
+            }
             if (lane == src) { w1 = r1; w2 = r2; }
         }
         // publish the two new known pixels and enqueue the children that still straddle a boundary
@@ -600,11 +673,12 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
             pending = __ballot_sync(0xffffffffu, !done);
         }
         __syncwarp();
-        if (act) f[q] = val;
+        if (act) {
+            out[q] = (float)val;                              // < 2^24: exact in fp32
+            if (q >= win_lo && q < win_hi) f[q] = val;        // only window columns can be referenced again
+        }
         __syncwarp();
     }
-    // ---- store (values < 2^24: exact in fp32) ----
-    for (int x = lane; x < n; x += 32) out[x] = f[x] >= kBigF ? FLT_MAX : (float)f[x];
 }
 
 // K2b (L1): second pass of the L1 transform (core/imgproc.h:137-146,178-184) along x on the u16
@@ -629,6 +703,59 @@ __global__ void __launch_bounds__(128) dt_row_l1_kernel(const uint16_t* __restri
     for (int x = dm.W - 1; x >= 0; --x) {
         cur = min(tmp[x], cur + 1);
         out[x] = cur >= (BIG >> 1) ? FLT_MAX : (float)cur;
+    }
+}
+
+// K2b (L1), warp per row: out[x] = min(x + min_{v<=x}(g[v]-v), -x + min_{v>=x}(g[v]+v)) with warp prefix / suffix
+// min scans (integers: exact); the forward result is parked in shared memory between the two sweeps.
+__global__ void __launch_bounds__(128) dt_row_l1_warp_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
+                                                             MapDims dm, int n_rows_total) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int* fwd = reinterpret_cast<int*>(smem_raw) + (size_t)warp * dm.pitch;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= n_rows_total) return;
+    const int n = dm.W;
+    const uint16_t* gin = g + (size_t)row * dm.pitch;
+    float* out = planes + (size_t)row * dm.pitch;
+    const int BIG = 1 << 28;
+    int carry = BIG;   // min over previous chunks of g[v] - v
+    for (int x0 = 0; x0 < n; x0 += 32) {
+        const int x = x0 + lane;
+        int a = BIG;
+        if (x < n) {
+            const int gv = gin[x];
+            a = gv == kNoEdge16 ? BIG : gv - x;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, a, o);
+            if (lane >= o) a = min(a, t);
+        }
+        a = min(a, carry);
+        if (x < n) fwd[x] = a;
+        carry = __shfl_sync(0xffffffffu, a, 31);
+    }
+    __syncwarp();
+    carry = BIG;       // min over later chunks of g[v] + v
+    for (int x0 = ((n - 1) >> 5) << 5; x0 >= 0; x0 -= 32) {
+        const int x = x0 + lane;
+        int b = BIG;
+        if (x < n) {
+            const int gv = gin[x];
+            b = gv == kNoEdge16 ? BIG : gv + x;
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_down_sync(0xffffffffu, b, o);
+            if (lane + o < 32) b = min(b, t);
+        }
+        b = min(b, carry);
+        if (x < n) {
+            const int v = min(fwd[x] + x, b - x);
+            out[x] = v >= (BIG >> 1) ? FLT_MAX : (float)v;
+        }
+        carry = __shfl_sync(0xffffffffu, b, 0);
     }
 }
 
@@ -861,19 +988,42 @@ void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, f
         dt_pass_literal_kernel<false><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
 }
 
-void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {
-    const int warps = 2;
-    const size_t smem = (size_t)warps * ((size_t)dm.pitch * 6 + 96 * 6 + 1024 * 4);
+void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, int col_lo, int col_hi, cudaStream_t s) {
+    // column window that can hold edge pixels, widened to multiples of 32
+    int win_lo = (col_lo < 0 ? 0 : col_lo) & ~31;
+    int win_hi = ((col_hi >= dm.W ? dm.W - 1 : col_hi) + 32) & ~31;
+    if (win_hi > dm.pitch) win_hi = dm.pitch;
+    if (win_hi <= win_lo) { win_lo = 0; win_hi = dm.pitch; }
+    const int win_w = win_hi - win_lo;
+    const size_t per_warp = (size_t)win_w * 4 + (size_t)dm.pitch * 2 + 96 * 6 + 1024 * 4;
+    // as many rows in flight per SM as shared memory allows (227 KB, 1 KB reserved per CTA)
+    int warps = 4;
+    int best_rows = 0;
+    for (int w = 1; w <= 4; ++w) {
+        const int ctas = (int)((227 * 1024) / (per_warp * w + 1024));
+        if (ctas * w > best_rows) { best_rows = ctas * w; warps = w; }
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(dt_row_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         attr_set = true;
     }
     const int rows = dm.D * dm.H;
-    dt_row_exact_kernel<<<cdiv(rows, warps), warps * 32, smem, s>>>(d_g, d_planes, dm, rows);
+    dt_row_exact_kernel<<<cdiv(rows, warps), warps * 32, per_warp * warps, s>>>(d_g, d_planes, dm, rows, win_lo, win_w);
 }
 
 void launch_dt_row_l1(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {
+    const size_t per_warp = (size_t)dm.pitch * 4;
+    if (per_warp * 4 <= 200 * 1024) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(dt_row_l1_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+            attr_set = true;
+        }
+        const int rows = dm.D * dm.H;
+        dt_row_l1_warp_kernel<<<cdiv(rows, 4), 128, per_warp * 4, s>>>(d_g, d_planes, dm, rows);
+        return;
+    }
     dim3 grid(cdiv(dm.H, 128), dm.D);
     dt_row_l1_kernel<<<grid, 128, 0, s>>>(d_g, d_planes, dm);
 }

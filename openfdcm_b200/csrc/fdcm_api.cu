@@ -191,6 +191,7 @@ struct fdcm_dt3 {
     MapDims dm{};
     float shift[2] = {0.f, 0.f};
     bool exact = true;
+    int col_lo = 0, col_hi = 0;  // column range that can hold edge pixels (bbox of the shifted scene)
     bool row_literal = false;   // FDCM_ROW_LITERAL=1: use the literal row pass even in the exact regime (A/B testing)
     int n_lines = 0;
     std::vector<float> keys;
@@ -294,6 +295,18 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
         ts[2 * i + 1] = scene[2 * i + 1] + m->shift[1];
     }
     for (int i = 0; i < n_lines; ++i) m->scene_bins[i] = bin_of_line(m->keys.data(), D, &ts[4 * (size_t)i]);
+    {
+        // clipping only moves end points inwards and pixels are round()ed coordinates: every edge pixel column lies in
+        // [floor(min x), ceil(max x)] of the shifted scene
+        float mnx = ts[0], mxx = ts[0];
+        for (int64_t i = 0; i < 2 * (int64_t)n_lines; ++i) {
+            mnx = std::min(mnx, ts[2 * i]);
+            mxx = std::max(mxx, ts[2 * i]);
+        }
+        const double lo = std::floor((double)mnx) - 1.0, hi = std::ceil((double)mxx) + 1.0;
+        m->col_lo = (lo < 0.0 || !(lo == lo)) ? 0 : (lo > dm.W - 1 ? dm.W - 1 : (int)lo);
+        m->col_hi = (!(hi == hi) || hi > dm.W - 1) ? dm.W - 1 : (hi < 0.0 ? 0 : (int)hi);
+    }
 
     // tables
     m->table = build_slope_table(m->keys.data(), D);
@@ -360,7 +373,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             launch_dt_pass_literal(true, true, m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->stack.p, s);
         } else {
             KernelScope k("dt_row_exact", N / 2 + N, s);
-            launch_dt_row_exact(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
+            launch_dt_row_exact(m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->col_lo, m->col_hi, s);
         }
     } else {
         {
@@ -1058,7 +1071,7 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
     if (e == cudaSuccess) {
         KernelScope k(literal ? "dt_row_literal" : "dt_row_exact", 0.0, s);
         if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
-        else launch_dt_row_exact(dg.as<uint16_t>(), dp.as<float>(), dm, s);
+        else launch_dt_row_exact(dg.as<uint16_t>(), dp.as<float>(), dm, 0, dm.W - 1, s);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(out, (size_t)n * 4, dp.p, (size_t)dm.pitch * 4, (size_t)n * 4, n_rows, cudaMemcpyDeviceToHost, s);
