@@ -919,16 +919,22 @@ __global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict_
         for (int r = r_lo; r < r_hi; ++r, gp += dm.pitch)
             if ((unsigned)(r - off) < 32u) tile[r * kTilePitch + lane] = *gp;
         __syncwarp();
-        // ---- sequential sums: lane = chain ----
+        // ---- sequential sums: lane = chain; the 32 tile values of the chain go through registers ----
         const int ncols = min(32, dm.W - i0);
-        for (int j = 0; j < ncols; ++j) {
+        float v[32];
+        int rr[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
             const int r = lane + __shfl_sync(0xffffffffu, off, j);         // tile row of this lane's chain in column j
-            if (r >= r_lo && r < r_hi) {
-                float* t = tile + r * kTilePitch + j;
-                const float a = *t;
-                if (have) { acc = a + acc; *t = acc; }
-                else { acc = a; have = true; }
-            } else {
+            rr[j] = (j < ncols && r >= r_lo && r < r_hi) ? r * kTilePitch + j : -1;
+            v[j] = rr[j] >= 0 ? tile[rr[j]] : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            if (rr[j] >= 0) {
+                if (have) { acc = v[j] + acc; tile[rr[j]] = acc; }
+                else { acc = v[j]; have = true; }
+            } else if (j < ncols) {
                 have = false;
             }
         }
