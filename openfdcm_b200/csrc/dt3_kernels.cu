@@ -647,6 +647,18 @@ __global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __res
         // owner(q) = owner of the nearest known pixel at or left of q
         const unsigned pv = act ? pt[q] : kUnknown;
         const unsigned known = __ballot_sync(0xffffffffu, pv != kUnknown);
+        if (known == 0) {
+            // whole chunk inside one run (owner = carry): one broadcast read, no dependencies.  If the owner pixel is
+            // in this chunk it owns itself, so its slot is rewritten with the same value (f[carry] + 0)
+            if (act) {
+                const int dd = q - carry;
+                const uint32_t vv = f[carry] + (uint32_t)(dd * dd);
+                out[q] = (float)vv;
+                if (q >= win_lo && q < win_hi) f[q] = vv;
+            }
+            __syncwarp();
+            continue;
+        }
         const unsigned le = known & (0xFFFFFFFFu >> (31 - lane));
         const int srcl = le ? 31 - __clz(le) : 0;
         const int ul = __shfl_sync(0xffffffffu, (int)pv, srcl);
