@@ -479,7 +479,7 @@ __device__ __forceinline__ int scan_owner(const uint32_t* f, int q, int lo, int 
     return arg;
 }
 
-constexpr int kQueueCap = 1024;   // intervals in flight per row (power of two)
+constexpr int kQueueCap = 256;   // intervals in flight per row (power of two)
 constexpr uint16_t kUnknown = 0xFFFFu;
 
 // Interval refinement.  pt[q] holds the owner of q at "known" pixels (0xFFFF elsewhere).  An interval (a, b) of known
@@ -1013,7 +1013,7 @@ void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm
     if (win_hi > dm.pitch) win_hi = dm.pitch;
     if (win_hi <= win_lo) { win_lo = 0; win_hi = dm.pitch; }
     const int win_w = win_hi - win_lo;
-    const size_t per_warp = (size_t)win_w * 4 + (size_t)dm.pitch * 2 + 96 * 6 + 1024 * 4;
+    const size_t per_warp = (size_t)win_w * 4 + (size_t)dm.pitch * 2 + 96 * 6 + 256 * 4;
     // as many rows in flight per SM as shared memory allows (227 KB, 1 KB reserved per CTA)
     int warps = 4;
     int best_rows = 0;
