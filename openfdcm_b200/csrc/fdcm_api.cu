@@ -4,6 +4,8 @@
 // There is deliberately no CPU compute path here: if CUDA is unavailable every entry point fails.
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -206,6 +208,8 @@ struct fdcm_dt3 {
     mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
         s_topk_out, s_topk_n, s_keys, s_keys2, s_idx, s_perm, s_sort_tmp;
     mutable float s_scene_min[2] = {0.f, 0.f}, s_scene_max[2] = {0.f, 0.f};   // bbox of the resident search scene
+    mutable std::mutex host_tset_mutex;
+    mutable fdcm_templates* host_tset = nullptr;   // reusable template set of fdcm_search_host
     mutable int32_t s_scene_n = 0;      // scene lines currently resident for the search (original, un-shifted)
     mutable int64_t last_n_hyp = 0;
     mutable fdcm_search_stats last_stats{};
@@ -219,7 +223,9 @@ struct fdcm_dt3 {
                           &s_perm, &s_sort_tmp})
             b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
+        destroy_host_tset();
     }
+    void destroy_host_tset();
 };
 
 // scene length ordering of establishSearchStrategy (defaultsearch.cpp:32-36) + upload of the original scene
@@ -646,6 +652,8 @@ struct fdcm_templates {
     int64_t n_lines = 0;
     std::vector<int32_t> offsets;     // host copy
     std::vector<float> lengths;       // getTemplateLengths
+    std::vector<float> h_line_len;    // host scratch kept for reloads
+    std::vector<int32_t> h_argsort;
     DevBuf lines, offs, argsort, line_len, denom;
     int denom_kind = -1;
     float denom_tau = 0.f;
@@ -656,6 +664,86 @@ struct fdcm_templates {
     }
 };
 
+// small persistent worker pool for the O(#templates) host preparation (std::sort per template)
+class HostPool {
+    std::vector<std::thread> workers_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    std::function<void(int, int)> job_;
+    int n_items_ = 0, chunk_ = 1, generation_ = 0, pending_ = 0;
+    std::atomic<int> next_{0};
+    bool stop_ = false;
+
+    void run() {
+        int seen = 0;
+        for (;;) {
+            std::function<void(int, int)> job;
+            int n, chunk;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                job = job_;
+                n = n_items_;
+                chunk = chunk_;
+            }
+            for (;;) {
+                const int b = next_.fetch_add(chunk);
+                if (b >= n) break;
+                job(b, std::min(n, b + chunk));
+            }
+            std::lock_guard<std::mutex> lk(mu_);
+            if (--pending_ == 0) done_cv_.notify_all();
+        }
+    }
+
+public:
+    explicit HostPool(int n) {
+        for (int i = 0; i < n; ++i) workers_.emplace_back([this] { run(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    // fn(begin, end) over [0, n) in chunks; the calling thread participates
+    void parallel_for(int n, int chunk, const std::function<void(int, int)>& fn) {
+        if (workers_.empty() || n <= chunk) { fn(0, n); return; }
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = fn;
+            n_items_ = n;
+            chunk_ = chunk;
+            next_.store(0);
+            pending_ = (int)workers_.size();
+            ++generation_;
+        }
+        cv_.notify_all();
+        for (;;) {
+            const int b = next_.fetch_add(chunk);
+            if (b >= n) break;
+            fn(b, std::min(n, b + chunk));
+        }
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+    }
+};
+
+static HostPool& host_pool() {
+    static HostPool pool((int)std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
+    return pool;
+}
+static std::mutex g_pool_mutex;   // one parallel_for at a time
+
+void fdcm_dt3::destroy_host_tset() {
+    delete host_tset;
+    host_tset = nullptr;
+}
+
 static void template_host_prep(const float* tl, const int32_t* off, int32_t T, std::vector<float>& line_len,
                                std::vector<int32_t>& argsort, std::vector<float>& lengths) {
     const int64_t n = off[T];
@@ -665,42 +753,37 @@ static void template_host_prep(const float* tl, const int32_t* off, int32_t T, s
     auto work = [&](int t0, int t1) {
         for (int t = t0; t < t1; ++t) {
             const int l0 = off[t], L = off[t + 1] - off[t];
-            for (int i = 0; i < L; ++i) line_len[(size_t)l0 + i] = line_length(tl + 4 * ((size_t)l0 + i));
-            const std::vector<long> idx = argsort_desc(line_len.data() + l0, L);   // defaultsearch.cpp:35
-            for (int i = 0; i < L; ++i) argsort[(size_t)l0 + i] = (int32_t)idx[(size_t)i];
-            lengths[(size_t)t] = eigen_sum(line_len.data() + l0, L);              // math.h:319-324
+            float* len = line_len.data() + l0;
+            int32_t* idx = argsort.data() + l0;
+            for (int i = 0; i < L; ++i) {
+                len[i] = line_length(tl + 4 * ((size_t)l0 + i));
+                idx[i] = i;
+            }
+            // argsort(tmpl_lengths, std::greater<>()) (defaultsearch.cpp:35, math.h:107-116): same std::sort, same comparator
+            std::sort(idx, idx + L, [len](int32_t const i1, int32_t const i2) { return len[i1] > len[i2]; });
+            lengths[(size_t)t] = eigen_sum(len, L);   // math.h:319-324
         }
     };
-    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
-    const int nt = (T >= 512) ? std::min(hw, 16) : 1;
-    if (nt <= 1) { work(0, T); return; }
-    std::vector<std::thread> th;
-    for (int i = 0; i < nt; ++i) th.emplace_back(work, (int)((int64_t)T * i / nt), (int)((int64_t)T * (i + 1) / nt));
-    for (auto& t : th) t.join();
+    if (T < 256) { work(0, T); return; }
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    host_pool().parallel_for(T, 64, work);
 }
 
-extern "C" fdcm_status fdcm_templates_create(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, int32_t device,
-                                             fdcm_templates** out) {
-    if (!out) return fail(FDCM_ERR_INVALID, "out is null");
-    *out = nullptr;
+// (re)load a template set into an existing object: device buffers grow only, host scratch is reused
+static fdcm_status templates_load(fdcm_templates* t, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                                  cudaStream_t s) {
     if (n_tmpl < 0 || !tmpl_offsets) return fail(FDCM_ERR_INVALID, "bad template offsets");
-    for (int t = 0; t < n_tmpl; ++t)
-        if (tmpl_offsets[t + 1] < tmpl_offsets[t]) return fail(FDCM_ERR_INVALID, "template offsets must be non-decreasing");
+    for (int i = 0; i < n_tmpl; ++i)
+        if (tmpl_offsets[i + 1] < tmpl_offsets[i]) return fail(FDCM_ERR_INVALID, "template offsets must be non-decreasing");
     const int64_t n = tmpl_offsets[n_tmpl];
     if (n > 0 && !tmpl_lines) return fail(FDCM_ERR_INVALID, "tmpl_lines is null");
-    CUDA_TRY(cudaSetDevice(device));
-    cudaStream_t s;
-    if (fdcm_status st = get_stream(device, &s)) return st;
-    fdcm_templates* t = new (std::nothrow) fdcm_templates();
-    if (!t) return fail(FDCM_ERR_NOMEM, "host allocation failed");
-    t->device = device;
     t->n_tmpl = n_tmpl;
     t->n_lines = n;
+    t->max_lines = 0;
+    t->denom_kind = -1;
     t->offsets.assign(tmpl_offsets, tmpl_offsets + n_tmpl + 1);
     for (int i = 0; i < n_tmpl; ++i) t->max_lines = std::max(t->max_lines, tmpl_offsets[i + 1] - tmpl_offsets[i]);
-    std::vector<float> line_len;
-    std::vector<int32_t> argsort;
-    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, line_len, argsort, t->lengths);
+    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, t->h_line_len, t->h_argsort, t->lengths);
     cudaError_t e = t->lines.reserve(std::max<size_t>(16, (size_t)n * 16));
     if (e == cudaSuccess) e = t->offs.reserve((size_t)(n_tmpl + 1) * 4);
     if (e == cudaSuccess) e = t->argsort.reserve(std::max<size_t>(4, (size_t)n * 4));
@@ -708,13 +791,31 @@ extern "C" fdcm_status fdcm_templates_create(const float* tmpl_lines, const int3
     if (e == cudaSuccess) e = t->denom.reserve(std::max<size_t>(4, (size_t)n_tmpl * 4));
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->lines.p, tmpl_lines, (size_t)n * 16, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) e = cudaMemcpyAsync(t->offs.p, tmpl_offsets, (size_t)(n_tmpl + 1) * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->argsort.p, argsort.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->line_len.p, line_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) {
-        delete t;
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->argsort.p, t->h_argsort.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->line_len.p, t->h_line_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    // no synchronisation needed: pageable sources are staged by the runtime before the call returns, and every
+    // consumer runs on the same stream
+    if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? FDCM_ERR_NOMEM : FDCM_ERR_CUDA,
-                    std::string("templates_create: ") + cudaGetErrorString(e));
+                    std::string("templates_load: ") + cudaGetErrorString(e));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_templates_create(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, int32_t device,
+                                             fdcm_templates** out) {
+    if (!out) return fail(FDCM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(device, &s)) return st;
+    fdcm_templates* t = new (std::nothrow) fdcm_templates();
+    if (!t) return fail(FDCM_ERR_NOMEM, "host allocation failed");
+    t->device = device;
+    fdcm_status st = templates_load(t, tmpl_lines, tmpl_offsets, n_tmpl, s);
+    if (st == FDCM_OK && cudaStreamSynchronize(s) != cudaSuccess) st = fail(FDCM_ERR_CUDA, "templates_create: stream synchronisation failed");
+    if (st != FDCM_OK) {
+        delete t;
+        return st;
     }
     *out = t;
     return FDCM_OK;
@@ -993,12 +1094,17 @@ extern "C" fdcm_status fdcm_search_host(const fdcm_dt3* m, const float* tmpl_lin
     if (!m || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
     *n_out = 0;
     if (n_tmpl <= 0) return FDCM_OK;
-    fdcm_templates* t = nullptr;
-    fdcm_status st = fdcm_templates_create(tmpl_lines, tmpl_offsets, n_tmpl, m->device, &t);
-    if (st != FDCM_OK) return st;
-    st = fdcm_search(m, t, scene, n_scene, p, out, capacity, n_out);
-    fdcm_templates_release(t);
-    return st;
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    std::lock_guard<std::mutex> lk(m->host_tset_mutex);
+    if (!m->host_tset) {   // one reusable template set per map: no allocation in steady state
+        m->host_tset = new (std::nothrow) fdcm_templates();
+        if (!m->host_tset) return fail(FDCM_ERR_NOMEM, "host allocation failed");
+        m->host_tset->device = m->device;
+    }
+    if (fdcm_status st = templates_load(m->host_tset, tmpl_lines, tmpl_offsets, n_tmpl, s)) return st;
+    return fdcm_search(m, m->host_tset, scene, n_scene, p, out, capacity, n_out);
 }
 
 extern "C" fdcm_status fdcm_search_last_hypotheses(const fdcm_dt3* m, int32_t* out, int64_t capacity, int64_t* n_out) {
