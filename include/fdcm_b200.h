@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FDCM_B200_ABI_VERSION 1
+#define FDCM_B200_ABI_VERSION 2
 
 typedef enum fdcm_status {
     FDCM_OK = 0,
@@ -70,6 +70,10 @@ typedef struct fdcm_search_params {
     int32_t top_k;          /* 0 = every match in hypothesis order (the reference's search() result);
                                >0 = the top_k best (ascending score, ties by hypothesis order) */
     int32_t tmpl_idx_base;  /* added to tmpl_idx in the emitted matches (template sharding keeps global indices) */
+    /* ConcentricRangeStrategy (searchstrategies/concentricrange.h:35-60): when concentric != 0 only the scene lines whose
+     * centre lies at a radius in (low_radius - eps, high_radius) of (center_x, center_y) take part in the search */
+    int32_t concentric;
+    float center_x, center_y, low_radius, high_radius;
 } fdcm_search_params;
 
 typedef struct fdcm_dt3_info {
@@ -171,6 +175,11 @@ fdcm_status fdcm_search_last_stats(const fdcm_dt3* map, fdcm_search_stats* stats
 fdcm_status fdcm_default_search(const float* tmpl_xyxy, int32_t n_tmpl_lines, const float* scene_xyxy, int32_t n_scene,
                                 int32_t max_tmpl_lines, int32_t max_scene_lines, int32_t* out_pairs, int32_t capacity,
                                 int32_t* n_out);
+
+/* establishSearchStrategy<ConcentricRangeStrategy> for one template (concentricrange.cpp:29-60) */
+fdcm_status fdcm_concentric_search(const float* tmpl_xyxy, int32_t n_tmpl_lines, const float* scene_xyxy, int32_t n_scene,
+                                   int32_t max_tmpl_lines, int32_t max_scene_lines, float center_x, float center_y,
+                                   float low_radius, float high_radius, int32_t* out_pairs, int32_t capacity, int32_t* n_out);
 
 /* Parity hook: run the horizontal L2^2 pass (second _distanceTransformColumnPassL2 call, core/imgproc.h:91-130)
  * on n_rows arbitrary rows of u16 vertical distances g (0xFFFF = FLT_MAX), f = g*g.  literal = 1 selects the

@@ -185,7 +185,7 @@ inline std::vector<Match> search(int batch, const DefaultSearch& s, const Dt3Cud
     std::vector<float> flat;
     std::vector<int32_t> off;
     pack(templates, flat, off);
-    fdcm_search_params p{(int32_t)s.max_tmpl_lines, (int32_t)s.max_scene_lines, batch, penalty_kind, tau, top_k, 0};
+    fdcm_search_params p{(int32_t)s.max_tmpl_lines, (int32_t)s.max_scene_lines, batch, penalty_kind, tau, top_k, 0, 0, 0.f, 0.f, 0.f, 0.f};
     int64_t cap = top_k > 0 ? top_k : 0;
     if (top_k <= 0)
         for (const auto& t : templates) cap += 2 * (int64_t)std::min(t.size() / 4, s.max_tmpl_lines) * (int64_t)s.max_scene_lines;

@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import MATCH_DTYPE, FdcmError, check, lib, ptr
 
 __all__ = [
-    "distance", "Dt3CudaParameters", "Dt3Cuda", "build_cuda_featuremap", "ThreadPool", "DefaultSearch",
+    "distance", "Dt3CudaParameters", "Dt3Cuda", "build_cuda_featuremap", "ThreadPool", "DefaultSearch", "ConcentricRangeStrategy",
     "BatchOptimize", "DefaultOptimize", "DefaultMatch", "DefaultPenalty", "ExponentialPenalty", "Match",
     "TemplateSet", "search", "search_topk", "penalize", "get_template_lengths", "sort_matches", "evaluate",
     "minmax_translation", "get_feature_size", "establish_search_strategy", "optimize", "FdcmError", "MATCH_DTYPE",
@@ -196,6 +196,25 @@ class DefaultSearch:
         return self.max_scene_lines
 
 
+class ConcentricRangeStrategy(DefaultSearch):
+    """searchstrategies/concentricrange.h:35-60: DefaultSearch on the scene lines whose centre lies in a radius band."""
+
+    def __init__(self, max_tmpl_lines, max_scene_lines, center_position, low_boundary, high_boundary):
+        super().__init__(max_tmpl_lines, max_scene_lines)
+        c = np.asarray(center_position, np.float32).reshape(2)
+        self.center_position = c
+        self.low_boundary, self.high_boundary = float(low_boundary), float(high_boundary)
+
+    def get_center_position(self):
+        return self.center_position
+
+    def get_low_radius_boundary(self):
+        return self.low_boundary
+
+    def get_high_radius_boundary(self):
+        return self.high_boundary
+
+
 class BatchOptimize:
     """optimizestrategies/batchoptimize.h:8-23 (pool / num_threads accepted and ignored)."""
 
@@ -290,9 +309,12 @@ def _search_raw(featuremap, templates, scene, searcher, optimizer, penalty=None,
         raise TypeError("the CUDA search needs a Dt3Cuda feature map (build_cuda_featuremap)")
     tset = templates if isinstance(templates, TemplateSet) else TemplateSet(templates, featuremap.device)
     s = None if scene is None else _records(scene)   # None: the scene the map was built from, already resident
+    conc = isinstance(searcher, ConcentricRangeStrategy)
     p = _lib.SearchParams(searcher.max_tmpl_lines, searcher.max_scene_lines, int(optimizer.batch_size),
                           0 if penalty is None else penalty.kind, 0.0 if penalty is None else float(penalty.tau),
-                          int(top_k), int(tmpl_idx_base))
+                          int(top_k), int(tmpl_idx_base), 1 if conc else 0,
+                          float(searcher.center_position[0]) if conc else 0.0, float(searcher.center_position[1]) if conc else 0.0,
+                          searcher.low_boundary if conc else 0.0, searcher.high_boundary if conc else 0.0)
     if tset.n_tmpl == 0:
         return np.zeros(0, MATCH_DTYPE)
     cap = int(top_k) if top_k > 0 else 2 * tset.n_tmpl * max(1, min(searcher.max_tmpl_lines, tset.max_lines)) * max(
@@ -393,8 +415,13 @@ def establish_search_strategy(searcher, tmpl, scene):
     cap = max(1, searcher.max_tmpl_lines * searcher.max_scene_lines)
     out = np.zeros((cap, 2), np.int32)
     n = C.c_int32(0)
-    check(lib().fdcm_default_search(ptr(t), t.shape[0], ptr(s), s.shape[0], searcher.max_tmpl_lines,
-                                    searcher.max_scene_lines, ptr(out), cap, C.byref(n)))
+    if isinstance(searcher, ConcentricRangeStrategy):
+        check(lib().fdcm_concentric_search(ptr(t), t.shape[0], ptr(s), s.shape[0], searcher.max_tmpl_lines, searcher.max_scene_lines,
+                                           float(searcher.center_position[0]), float(searcher.center_position[1]),
+                                           searcher.low_boundary, searcher.high_boundary, ptr(out), cap, C.byref(n)))
+    else:
+        check(lib().fdcm_default_search(ptr(t), t.shape[0], ptr(s), s.shape[0], searcher.max_tmpl_lines,
+                                        searcher.max_scene_lines, ptr(out), cap, C.byref(n)))
     return out[: n.value].copy()
 
 

@@ -22,7 +22,8 @@ class Dt3Params(C.Structure):
 class SearchParams(C.Structure):
     _fields_ = [("max_tmpl_lines", C.c_int32), ("max_scene_lines", C.c_int32), ("batch_size", C.c_int32),
                 ("penalty_kind", C.c_int32), ("penalty_tau", C.c_float), ("top_k", C.c_int32),
-                ("tmpl_idx_base", C.c_int32)]
+                ("tmpl_idx_base", C.c_int32), ("concentric", C.c_int32), ("center_x", C.c_float), ("center_y", C.c_float),
+                ("low_radius", C.c_float), ("high_radius", C.c_float)]
 
 
 class Dt3Info(C.Structure):
@@ -69,6 +70,8 @@ SIGNATURES = {
     "fdcm_default_search": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32,
                                       C.POINTER(C.c_int32)]),
     "fdcm_debug_dt_rows": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "fdcm_concentric_search": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "fdcm_orientation_bins": (C.c_int, [C.c_int32, _P, C.c_int32, _P, _P]),
     "fdcm_penalize": (C.c_int, [C.c_int32, C.c_float, _P, C.c_int64, _P, C.c_int64]),
     "fdcm_sort_matches": (C.c_int, [_P, C.c_int64]),

@@ -211,6 +211,11 @@ struct fdcm_dt3 {
     mutable std::mutex host_tset_mutex;
     mutable fdcm_templates* host_tset = nullptr;   // reusable template set of fdcm_search_host
     mutable int32_t s_scene_n = 0;      // scene lines currently resident for the search (original, un-shifted)
+    mutable int32_t s_sorted_n = 0;     // entries of the resident length ordering (== s_scene_n unless radius-filtered)
+    mutable bool s_resident_is_build = false;   // the resident search scene is the scene the map was built from
+    mutable bool s_filter_on = false;
+    mutable float s_filter[4] = {0.f, 0.f, 0.f, 0.f};
+    std::vector<float> h_build_scene;   // host copy of the build scene (for scene == NULL searches with a new filter)
     mutable int64_t last_n_hyp = 0;
     mutable fdcm_search_stats last_stats{};
     mutable void* h_pinned = nullptr;   // pinned staging for match download
@@ -228,18 +233,41 @@ struct fdcm_dt3 {
     void destroy_host_tset();
 };
 
-// scene length ordering of establishSearchStrategy (defaultsearch.cpp:32-36) + upload of the original scene
-static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, int32_t n_scene, cudaStream_t s) {
-    std::vector<float> slen((size_t)n_scene);
-    for (int i = 0; i < n_scene; ++i) slen[(size_t)i] = line_length(scene + 4 * (size_t)i);
-    const std::vector<long> sidx = argsort_desc(slen.data(), n_scene);
-    std::vector<float> sorted_len((size_t)n_scene);
-    std::vector<int32_t> sorted_idx((size_t)n_scene);
-    for (int i = 0; i < n_scene; ++i) {
+struct SceneFilter { bool on; float cx, cy, lo, hi; };
+
+// filterInRange (searchstrategies/concentricrange.h:73-84)
+static std::vector<int32_t> filter_in_range(const float* lines, int32_t n, const SceneFilter& f) {
+    std::vector<int32_t> idx;
+    for (int32_t i = 0; i < n; ++i) {
+        const float* l = lines + 4 * (size_t)i;
+        const float mx = (l[2] + l[0]) / 2 - f.cx, my = (l[3] + l[1]) / 2 - f.cy;
+        const float rad = std::sqrt(mx * mx + my * my);
+        if (rad > (f.lo - std::numeric_limits<float>::epsilon()) && rad < f.hi) idx.push_back(i);
+    }
+    return idx;
+}
+
+// scene length ordering of establishSearchStrategy (defaultsearch.cpp:32-36; concentricrange.cpp:33-45 when a radius
+// filter is given: ordering of the filtered lines, indices mapped back to the original scene) + upload of the scene
+static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, int32_t n_scene, const SceneFilter& flt, cudaStream_t s) {
+    std::vector<int32_t> subset;
+    if (flt.on) subset = filter_in_range(scene, n_scene, flt);
+    else {
+        subset.resize((size_t)n_scene);
+        for (int i = 0; i < n_scene; ++i) subset[(size_t)i] = i;
+    }
+    const int ns = (int)subset.size();
+    std::vector<float> slen((size_t)ns);
+    for (int i = 0; i < ns; ++i) slen[(size_t)i] = line_length(scene + 4 * (size_t)subset[(size_t)i]);
+    const std::vector<long> sidx = argsort_desc(slen.data(), ns);
+    std::vector<float> sorted_len((size_t)ns);
+    std::vector<int32_t> sorted_idx((size_t)ns);
+    for (int i = 0; i < ns; ++i) {
         sorted_len[(size_t)i] = slen[(size_t)sidx[(size_t)i]];
-        sorted_idx[(size_t)i] = (int32_t)sidx[(size_t)i];
+        sorted_idx[(size_t)i] = subset[(size_t)sidx[(size_t)i]];
     }
     m->s_scene_n = 0;
+    m->s_sorted_n = 0;
     m->s_scene_min[0] = m->s_scene_max[0] = scene[0];
     m->s_scene_min[1] = m->s_scene_max[1] = scene[1];
     for (int64_t i = 0; i < 2 * (int64_t)n_scene; ++i)
@@ -249,13 +277,18 @@ static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, in
             if (v > m->s_scene_max[a]) m->s_scene_max[a] = v;
         }
     CUDA_TRY(m->s_scene.reserve((size_t)n_scene * 16));
-    CUDA_TRY(m->s_sorted_len.reserve((size_t)n_scene * 4));
-    CUDA_TRY(m->s_sorted_idx.reserve((size_t)n_scene * 4));
+    CUDA_TRY(m->s_sorted_len.reserve(std::max<size_t>(4, (size_t)ns * 4)));
+    CUDA_TRY(m->s_sorted_idx.reserve(std::max<size_t>(4, (size_t)ns * 4)));
     CUDA_TRY(cudaMemcpyAsync(m->s_scene.p, scene, (size_t)n_scene * 16, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, sorted_len.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, sorted_idx.data(), (size_t)n_scene * 4, cudaMemcpyHostToDevice, s));
+    if (ns) {
+        CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, sorted_len.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, sorted_idx.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, s));
+    }
     CUDA_TRY(cudaStreamSynchronize(s));   // pageable temporaries
     m->s_scene_n = n_scene;
+    m->s_sorted_n = ns;
+    m->s_filter_on = flt.on;
+    m->s_filter[0] = flt.cx; m->s_filter[1] = flt.cy; m->s_filter[2] = flt.lo; m->s_filter[3] = flt.hi;
     return FDCM_OK;
 }
 
@@ -267,6 +300,8 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     m->scene_bins.clear();
     if (n_lines == 0) {   // dt3cpu.h:180-181: empty map, translation (0,0), size (0,0)
         m->s_scene_n = 0;
+        m->s_sorted_n = 0;
+        m->h_build_scene.clear();
         m->dm = MapDims{0, 0, 0, 0, 0, 0};
         m->shift[0] = m->shift[1] = 0.f;
         m->keys.clear();
@@ -349,7 +384,9 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     CUDA_TRY(cudaStreamSynchronize(s));   // ts / scene_bins are pageable temporaries
     // keep the original scene resident for searches that pass scene == NULL
     std::lock_guard<std::mutex> lk(m->search_mutex);
-    return upload_search_scene(m, scene, n_lines, s);
+    m->h_build_scene.assign(scene, scene + 4 * (size_t)n_lines);
+    m->s_resident_is_build = true;
+    return upload_search_scene(m, scene, n_lines, SceneFilter{false, 0, 0, 0, 0}, s);
 }
 
 static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
@@ -865,7 +902,10 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     m->last_stats = fdcm_search_stats{0, 0, 0, 0};
     // defaultmatch.cpp:40-41
     const bool resident_scene = scene == nullptr;
-    if (resident_scene) n_scene = m->s_scene_n;
+    if (resident_scene) {
+        scene = m->h_build_scene.data();
+        n_scene = (int32_t)(m->h_build_scene.size() / 4);
+    }
     if (t->n_tmpl == 0 || n_scene <= 0 || (m->dm.W == 0 && m->dm.H == 0)) return FDCM_OK;
     if (m->stage != 0) return fail(FDCM_ERR_INVALID, "feature map was built with a debug stage");
     CUDA_TRY(cudaSetDevice(m->device));
@@ -873,8 +913,15 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     if (fdcm_status st = get_stream(m->device, &s)) return st;
 
     // ---- host prep: scene length order (defaultsearch.cpp:32-36) and hypothesis offsets ----
-    if (!resident_scene)
-        if (fdcm_status st = upload_search_scene(m, scene, n_scene, s)) return st;
+    const SceneFilter flt{p->concentric != 0, p->center_x, p->center_y, p->low_radius, p->high_radius};
+    const bool same_filter = flt.on == m->s_filter_on && (!flt.on || (flt.cx == m->s_filter[0] && flt.cy == m->s_filter[1] &&
+                                                                      flt.lo == m->s_filter[2] && flt.hi == m->s_filter[3]));
+    if (!(resident_scene && m->s_resident_is_build && same_filter)) {
+        if (fdcm_status st = upload_search_scene(m, scene, n_scene, flt, s)) return st;
+        m->s_resident_is_build = resident_scene;
+    }
+    n_scene = m->s_sorted_n;   // the lines that take part in the length matching
+    if (n_scene <= 0) return FDCM_OK;   // concentricrange.cpp:37-38
     const int nS = std::min<int>(n_scene, p->max_scene_lines);
     std::vector<int64_t> hyp_off((size_t)t->n_tmpl + 1, 0);
     for (int i = 0; i < t->n_tmpl; ++i) {
@@ -922,7 +969,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     sv.lines = m->s_scene.as<float4>();
     sv.sorted_len = m->s_sorted_len.as<float>();
     sv.sorted_idx = m->s_sorted_idx.as<int32_t>();
-    sv.n = n_scene;
+    sv.n = n_scene;   // number of length-ordered (possibly radius-filtered) lines; lines[] holds the whole scene
     SearchLaunch sl;
     sl.max_tmpl_lines = p->max_tmpl_lines;
     sl.max_scene_lines = p->max_scene_lines;
@@ -1156,6 +1203,28 @@ extern "C" fdcm_status fdcm_default_search(const float* tmpl, int32_t L, const f
     }
     *n_out = n;
     if (n > capacity) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_concentric_search(const float* tmpl, int32_t L, const float* scene, int32_t M, int32_t maxT, int32_t maxS,
+                                              float cx, float cy, float lo, float hi, int32_t* out_pairs, int32_t capacity, int32_t* n_out) {
+    if (!n_out || L < 0 || M < 0) return fail(FDCM_ERR_INVALID, "bad argument");
+    *n_out = 0;
+    if (L == 0 || M == 0) return FDCM_OK;
+    if (!tmpl || !scene) return fail(FDCM_ERR_INVALID, "null argument");
+    const std::vector<int32_t> subset = filter_in_range(scene, M, SceneFilter{true, cx, cy, lo, hi});
+    if (subset.empty()) return FDCM_OK;
+    std::vector<float> fs;
+    for (int32_t i : subset) fs.insert(fs.end(), scene + 4 * (size_t)i, scene + 4 * (size_t)i + 4);
+    int32_t n = 0;
+    std::vector<int32_t> pairs((size_t)std::max(1, capacity) * 2);
+    fdcm_status st = fdcm_default_search(tmpl, L, fs.data(), (int32_t)subset.size(), maxT, maxS, pairs.data(), capacity, &n);
+    *n_out = n;
+    if (st != FDCM_OK) return st;
+    for (int32_t i = 0; i < n; ++i) {
+        out_pairs[2 * i] = pairs[2 * (size_t)i];
+        out_pairs[2 * i + 1] = subset[(size_t)pairs[2 * (size_t)i + 1]];
+    }
     return FDCM_OK;
 }
 

@@ -616,15 +616,45 @@ static void getCenteredRange(size_t center, size_t vec_size, size_t max_length, 
 
 struct Combo { long tmplLine, sceneLine; };
 
+// ConcentricRangeStrategy (searchstrategies/concentricrange.h:35-60): optional radius filter on the scene lines
+struct ConcFilter { bool on; float cx, cy, lo, hi; };
+
+// concentricrange.h:73-84 filterInRange
+static std::vector<long> filterInRange(const float* lines, Index n, float cx, float cy, float min_radius, float max_radius) {
+    std::vector<long> idx;
+    for (Index i = 0; i < n; ++i) {
+        const float* l = lines + 4 * i;
+        const float mx = (l[2] + l[0]) / 2 - cx, my = (l[3] + l[1]) / 2 - cy;   // getCenter - center_position
+        const float rad = std::sqrt(mx * mx + my * my);
+        if (rad > (min_radius - std::numeric_limits<float>::epsilon()) && rad < max_radius) idx.push_back((long)i);
+    }
+    return idx;
+}
+
 // defaultsearch.cpp:29-49
 static std::vector<Combo> establishSearchStrategy(size_t maxT, size_t maxS, const float* tmpl, Index L,
-                                                  const float* scene, Index M) {
+                                                  const float* scene_all, Index M_all, const ConcFilter* cf = nullptr) {
+    // concentricrange.cpp:29-60: filter, then the DefaultSearch procedure on the filtered lines, indices mapped back
+    std::vector<long> filt;
+    std::vector<float> fscene;
+    const float* scene = scene_all;
+    Index M = M_all;
+    if (cf && cf->on) {
+        filt = filterInRange(scene_all, M_all, cf->cx, cf->cy, cf->lo, cf->hi);
+        if (filt.empty()) return {};
+        for (long i : filt) fscene.insert(fscene.end(), scene_all + 4 * i, scene_all + 4 * i + 4);
+        scene = fscene.data();
+        M = (Index)filt.size();
+    }
     std::vector<float> sl(M), tl(L);
     for (Index i = 0; i < M; ++i) sl[i] = line_length(scene + 4 * i);
     for (Index i = 0; i < L; ++i) tl[i] = line_length(tmpl + 4 * i);
-    const std::vector<long> ss = argsort_desc(sl), st = argsort_desc(tl);
+    std::vector<long> ss = argsort_desc(sl);
+    const std::vector<long> st = argsort_desc(tl);
     std::vector<float> sorted_len(M);
     for (Index i = 0; i < M; ++i) sorted_len[i] = sl[ss[i]];
+    if (cf && cf->on)
+        for (auto& v : ss) v = filt[(size_t)v];   // initial_sorted_filtered_scene_idx
     std::vector<Combo> out;
     const size_t nt = std::min((size_t)L, maxT);
     for (size_t r = 0; r < nt; ++r) {
@@ -721,7 +751,8 @@ struct MatchRec { int32_t tmpl_idx; float score; float t[6]; };   // t = row-maj
 // defaultmatch.cpp:32-89
 static std::vector<MatchRec> search(const Dt3& fm, const float* tl, const int32_t* off, Index T, const float* scene,
                                     Index M, size_t maxT, size_t maxS, long batch, int nthreads,
-                                    std::vector<int32_t>* hyp_out /* optional: (tmpl, tmplLine, sceneLine, rev) */) {
+                                    std::vector<int32_t>* hyp_out /* optional: (tmpl, tmplLine, sceneLine, rev) */,
+                                    const ConcFilter* cf = nullptr) {
     std::vector<MatchRec> all;
     if (T == 0 || M == 0 || (fm.size[0] == 0 && fm.size[1] == 0)) return all;
     std::vector<std::vector<float>> aligned;
@@ -732,7 +763,7 @@ static std::vector<MatchRec> search(const Dt3& fm, const float* tl, const int32_
         const float* tmpl = tl + 4 * (size_t)off[t];
         const Index L = off[t + 1] - off[t];
         if (L == 0) continue;
-        for (const Combo& cb : establishSearchStrategy(maxT, maxS, tmpl, L, scene, M)) {
+        for (const Combo& cb : establishSearchStrategy(maxT, maxS, tmpl, L, scene, M, cf)) {
             const float* sline = scene + 4 * cb.sceneLine;
             const float* tline = tmpl + 4 * cb.tmplLine;
             float ax, ay;
@@ -926,6 +957,23 @@ int orc_default_search(const float* tmpl, int L, const float* scene, int M, uint
     return (int)v.size();
 }
 
+int orc_filter_in_range(const float* lines, int n, float cx, float cy, float lo, float hi, long* out) {
+    auto v = orc::filterInRange(lines, n, cx, cy, lo, hi);
+    for (size_t i = 0; i < v.size(); ++i) out[i] = v[i];
+    return (int)v.size();
+}
+
+int orc_concentric_search(const float* tmpl, int L, const float* scene, int M, uint64_t maxT, uint64_t maxS, float cx, float cy,
+                          float lo, float hi, long* out_pairs, int cap) {
+    const orc::ConcFilter cf{true, cx, cy, lo, hi};
+    auto v = orc::establishSearchStrategy((size_t)maxT, (size_t)maxS, tmpl, L, scene, M, &cf);
+    for (size_t i = 0; i < v.size() && (int)i < cap; ++i) {
+        out_pairs[2 * i] = v[i].tmplLine;
+        out_pairs[2 * i + 1] = v[i].sceneLine;
+    }
+    return (int)v.size();
+}
+
 void orc_centered_range(uint64_t c, uint64_t n, uint64_t len, uint64_t* b, uint64_t* e) {
     size_t bb, ee;
     orc::getCenteredRange((size_t)c, (size_t)n, (size_t)len, bb, ee);
@@ -946,10 +994,12 @@ int orc_optimize_one(const void* h, const float* tmpl, int L, const float* align
 // hyp (optional, 4 ints per hypothesis, capacity hyp_cap hypotheses) receives the hypothesis list.
 long orc_search(const void* h, const float* tmpl_lines, const int32_t* tmpl_offsets, int n_tmpl, const float* scene,
                 int n_scene, uint64_t maxT, uint64_t maxS, long batch, int nthreads, void* out_matches, long cap,
-                int32_t* hyp, long hyp_cap, long* n_hyp) {
+                int32_t* hyp, long hyp_cap, long* n_hyp, const float* concentric /* null or {cx, cy, lo, hi} */) {
     std::vector<int32_t> hv;
+    orc::ConcFilter cf{false, 0, 0, 0, 0};
+    if (concentric) cf = orc::ConcFilter{true, concentric[0], concentric[1], concentric[2], concentric[3]};
     auto m = orc::search(*(const orc::Dt3*)h, tmpl_lines, tmpl_offsets, n_tmpl, scene, n_scene, (size_t)maxT, (size_t)maxS,
-                         batch, nthreads, (hyp || n_hyp) ? &hv : nullptr);
+                         batch, nthreads, (hyp || n_hyp) ? &hv : nullptr, concentric ? &cf : nullptr);
     if (n_hyp) *n_hyp = (long)hv.size() / 4;
     if (hyp) std::memcpy(hyp, hv.data(), sizeof(int32_t) * std::min<size_t>(hv.size(), (size_t)hyp_cap * 4));
     const long n = (long)m.size();

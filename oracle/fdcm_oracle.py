@@ -190,6 +190,22 @@ def default_search(tmpl, scene, max_tmpl_lines, max_scene_lines):
     return out[:n].copy()   # rows = (tmplLineIdx, sceneLineIdx)
 
 
+def filter_in_range(lines, center, lo, hi):
+    r = lines_to_records(lines)
+    out = np.zeros(max(1, r.shape[0]), np.int64)
+    n = lib().orc_filter_in_range(_p(r), r.shape[0], C.c_float(center[0]), C.c_float(center[1]), C.c_float(lo), C.c_float(hi), _p(out))
+    return out[:n].tolist()
+
+
+def concentric_search(tmpl, scene, max_tmpl_lines, max_scene_lines, center, lo, hi):
+    t, s = lines_to_records(tmpl), lines_to_records(scene)
+    cap = int(max_tmpl_lines * max_scene_lines) + 1
+    out = np.zeros((cap, 2), np.int64)
+    n = lib().orc_concentric_search(_p(t), t.shape[0], _p(s), s.shape[0], C.c_uint64(max_tmpl_lines), C.c_uint64(max_scene_lines),
+                                    C.c_float(center[0]), C.c_float(center[1]), C.c_float(lo), C.c_float(hi), _p(out), cap)
+    return out[:n].copy()
+
+
 def centered_range(center, n, length):
     b, e = C.c_uint64(0), C.c_uint64(0)
     lib().orc_centered_range(C.c_uint64(center), C.c_uint64(n), C.c_uint64(length), C.byref(b), C.byref(e))
@@ -283,7 +299,7 @@ class Dt3Cpu:
         has = lib().orc_optimize_one(self._h, _p(r), r.shape[0], _p(av), C.c_long(batch), _p(out))
         return (bool(has), float(out[0]), out[1:].copy())
 
-    def search(self, templates, scene, max_tmpl_lines, max_scene_lines, batch=10, nthreads=0, want_hyp=False):
+    def search(self, templates, scene, max_tmpl_lines, max_scene_lines, batch=10, nthreads=0, want_hyp=False, concentric=None):
         """DefaultMatch search; batch<=0 selects DefaultOptimize. Returns MATCH_DTYPE array
         in hypothesis order (and optionally the (tmpl, tmplLine, sceneLine, rev) hypothesis list)."""
         flat, off = pack_templates(templates)
@@ -297,7 +313,8 @@ class Dt3Cpu:
         n_hyp = C.c_long(0)
         n = lib().orc_search(self._h, _p(flat), _p(off), T, _p(s), s.shape[0], C.c_uint64(max_tmpl_lines),
                              C.c_uint64(max_scene_lines), C.c_long(batch), int(nthreads), _p(out), C.c_long(cap),
-                             _p(hyp) if want_hyp else None, C.c_long(cap), C.byref(n_hyp) if want_hyp else None)
+                             _p(hyp) if want_hyp else None, C.c_long(cap), C.byref(n_hyp) if want_hyp else None,
+                             _p(_f32(concentric)) if concentric is not None else None)
         if want_hyp:
             return out[:n].copy(), hyp[:n_hyp.value].copy()
         return out[:n].copy()

@@ -31,12 +31,12 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/fdcm_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == declared
-    assert lib.fdcm_abi_version() == 1
+    assert lib.fdcm_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     assert C.sizeof(_lib.Dt3Params) == 16
-    assert C.sizeof(_lib.SearchParams) == 28
+    assert C.sizeof(_lib.SearchParams) == 48
     assert C.sizeof(_lib.Dt3Info) == 40
     assert C.sizeof(_lib.SearchStats) == 32
     assert _lib.MATCH_DTYPE.itemsize == 32
@@ -134,3 +134,15 @@ def test_cpp_host_mirror_builds_and_fails_loudly_without_gpu():
     if not torch.cuda.is_available():
         r = subprocess.run([exe], capture_output=True, text=True)
         assert r.returncode == 1 and "libfdcm_b200" in r.stdout
+
+
+def test_concentric_search_matches_oracle():
+    z = KATS["concentric_range"]["zero_centered"]
+    mt, ms, center, lo, hi = z["args"]
+    got = fdcm.establish_search_strategy(fdcm.ConcentricRangeStrategy(mt, ms, center, lo, hi), np.array(z["tmpl"], F32), np.array(z["scene"], F32))
+    assert len(got) == 4 and all(p in z["allowed"] for p in got.tolist())
+    scene = synth_scene(640, 480, 300, seed=14)
+    for tmpl in synth_templates(4, 30, 640, seed=15):
+        for lo_r, hi_r in ((0.0, 150.0), (100.0, 260.0), (5000.0, 6000.0)):
+            s = fdcm.ConcentricRangeStrategy(4, 6, (320, 240), lo_r, hi_r)
+            assert np.array_equal(fdcm.establish_search_strategy(s, tmpl, scene), orc.concentric_search(tmpl, scene, 4, 6, (320, 240), lo_r, hi_r))

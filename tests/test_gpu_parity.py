@@ -357,3 +357,21 @@ def test_config5_shape_multiview_batch():
         c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
         pen = orc.penalize(1, 1.5, c.search(tmpls, scene, 4, 4, batch=10), orc.template_lengths(tmpls))
         assert np.array_equal(top, pen[np.lexsort((np.arange(len(pen)), pen["score"]))[:10]]), f"scene {s}"
+
+
+def test_concentric_range_search_on_gpu():
+    """ConcentricRangeStrategy (concentricrange.cpp:29-60) through the fused CUDA search, incl. the resident-scene path
+    switching between filters and the empty-filter case."""
+    scene, tmpls = _workload(61, n_tmpl=10, n_lines=22)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    opt = fdcm.BatchOptimize(10)
+    for lo_r, hi_r in ((0.0, 150.0), (100.0, 260.0), (5000.0, 6000.0), (0.0, 150.0)):
+        s = fdcm.ConcentricRangeStrategy(4, 5, (320, 240), lo_r, hi_r)
+        for sc in (scene, None):
+            got = fdcm.search_all(g, tmpls, sc, s, opt)
+            want, hyp = c.search(tmpls, scene, 4, 5, batch=10, want_hyp=True, concentric=[320, 240, lo_r, hi_r])
+            assert np.array_equal(g.last_hypotheses().reshape(-1, 4), hyp.reshape(-1, 4))
+            assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
+    got = fdcm.search_all(g, tmpls, None, fdcm.DefaultSearch(4, 5), opt)      # back to the unfiltered ordering
+    assert np.array_equal(got["score"], c.search(tmpls, scene, 4, 5, batch=10)["score"])

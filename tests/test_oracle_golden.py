@@ -399,3 +399,16 @@ def test_eigen_sum_order():
             for v in c[n4:]:
                 r = F32(r + v)
         assert orc.eigen_sum(c) == float(r)
+
+
+def test_concentric_range_strategy():
+    """searchstrategy.test.cpp:91-160: filterInRange, empty inputs, 0-centred scene."""
+    c = KATS["concentric_range"]
+    f = c["filter"]
+    assert orc.filter_in_range(np.array(f["lines"], F32), f["center"], f["lo"], f["hi"]) == f["expect"]
+    z = c["zero_centered"]
+    mt, ms, center, lo, hi = z["args"]
+    got = orc.concentric_search(np.array(z["tmpl"], F32), np.array(z["scene"], F32), mt, ms, center, lo, hi)
+    assert len(got) == 4 and all(p in z["allowed"] for p in got.tolist())
+    assert len(orc.concentric_search(np.array(z["tmpl"], F32), np.zeros((4, 0), F32), mt, ms, center, lo, hi)) == 0
+    assert len(orc.concentric_search(np.zeros((4, 0), F32), np.array(z["scene"], F32), mt, ms, center, lo, hi)) == 0
