@@ -15,13 +15,14 @@ import enum
 import numpy as np
 
 from . import _lib
+from .io import read, write
 from ._lib import MATCH_DTYPE, FdcmError, check, lib, ptr
 
 __all__ = [
     "distance", "Dt3CudaParameters", "Dt3Cuda", "build_cuda_featuremap", "ThreadPool", "DefaultSearch", "ConcentricRangeStrategy",
     "BatchOptimize", "DefaultOptimize", "DefaultMatch", "DefaultPenalty", "ExponentialPenalty", "Match",
     "TemplateSet", "search", "search_topk", "penalize", "get_template_lengths", "sort_matches", "evaluate",
-    "minmax_translation", "get_feature_size", "establish_search_strategy", "optimize", "FdcmError", "MATCH_DTYPE",
+    "minmax_translation", "get_feature_size", "establish_search_strategy", "optimize", "read", "write", "FdcmError", "MATCH_DTYPE",
 ]
 
 

@@ -146,3 +146,21 @@ def test_concentric_search_matches_oracle():
         for lo_r, hi_r in ((0.0, 150.0), (100.0, 260.0), (5000.0, 6000.0)):
             s = fdcm.ConcentricRangeStrategy(4, 6, (320, 240), lo_r, hi_r)
             assert np.array_equal(fdcm.establish_search_strategy(s, tmpl, scene), orc.concentric_search(tmpl, scene, 4, 6, (320, 240), lo_r, hi_r))
+
+
+def test_packio_read_write_roundtrip(tmp_path):
+    """tests/python/test_matching.py:95-105 (write/read round trip) + decoding of a real reference asset."""
+    lines = create_lines(100, 10)
+    path = str(tmp_path / "test_write_array.lines")
+    fdcm.write(path, lines)
+    assert np.array_equal(fdcm.read(path), lines)
+    fdcm.write(path, np.zeros((4, 0)))                       # overwrite + empty
+    assert fdcm.read(path).shape == (4, 0)
+    with pytest.raises(RuntimeError):
+        fdcm.read(str(tmp_path / "missing.scene"))
+    real = os.path.join(ROOT, "tests", "golden", "real_obj_01")
+    scene = fdcm.read(os.path.join(real, "camera_0.scene"))
+    assert scene.shape == (4, 557) and scene.dtype == np.float32
+    assert 190 < scene.min() and scene.max() < 660
+    tm = fdcm.read(os.path.join(real, "templates", "template_0.tmpl"))
+    assert tm.shape[0] == 4 and 10 <= tm.shape[1] <= 40

@@ -375,3 +375,27 @@ def test_concentric_range_search_on_gpu():
             assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
     got = fdcm.search_all(g, tmpls, None, fdcm.DefaultSearch(4, 5), opt)      # back to the unfiltered ordering
     assert np.array_equal(got["score"], c.search(tmpls, scene, 4, 5, batch=10)["score"])
+
+
+def test_real_asset_regression():
+    """Real detected lines (reference notebooks/assets/obj_01: one 557-line scene, 24 templates) with the parameters of
+    notebooks/pose_extimation_example.ipynb: DefaultSearch(4,10), BatchOptimize(10), depth 30, coeff 5, padding 1.0, L2."""
+    import glob
+    import os
+    real = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_obj_01")
+    scene = fdcm.read(os.path.join(real, "camera_0.scene"))
+    tmpls = [fdcm.read(p) for p in sorted(glob.glob(os.path.join(real, "templates", "*.tmpl")))]
+    assert len(tmpls) == 24
+    for padding in (1.0, 2.2):
+        g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, padding))
+        c = orc.Dt3Cpu(scene, 30, 5.0, padding)
+        for d in (0, 9, 15, 27):
+            assert np.array_equal(g.plane(d), c.plane(d))
+        got = fdcm.search_all(g, tmpls, scene, fdcm.DefaultSearch(4, 10), fdcm.BatchOptimize(10))
+        want, hyp = c.search(tmpls, scene, 4, 10, batch=10, want_hyp=True)
+        assert np.array_equal(g.last_hypotheses(), hyp)
+        assert len(got) == len(want)
+        assert np.array_equal(got["score"], want["score"]) and np.array_equal(got["transform"], want["transform"])
+        top = fdcm.search_topk(g, tmpls, scene, fdcm.DefaultSearch(4, 10), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
+        pen = orc.penalize(1, 1.5, want, orc.template_lengths(tmpls))
+        assert np.array_equal(top, pen[np.lexsort((np.arange(len(pen)), pen["score"]))[:10]])
