@@ -182,7 +182,7 @@ def main():
     def step_e2e():
         import ctypes as C
         L = fdcm.lib()
-        fdcm.check(L.fdcm_dt3_rebuild(fm._h, h_scene.data_ptr(), h_scene.shape[0]))
+        fdcm.check(L.fdcm_dt3_rebuild_async(fm._h, h_scene.data_ptr(), h_scene.shape[0]))   # host prep of the search overlaps the build
         out = np.zeros(TOP_K, fdcm.MATCH_DTYPE)
         n = C.c_int64(0)
         p = fdcm._lib.SearchParams(MAX_T, MAX_S, BATCH, penalty.kind, penalty.tau, TOP_K, base, 0, 0.0, 0.0, 0.0, 0.0)

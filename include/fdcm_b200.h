@@ -112,6 +112,9 @@ fdcm_status fdcm_dt3_build(const float* scene_xyxy, int32_t n_lines, const fdcm_
                            int32_t stage, fdcm_dt3** out);
 /* Same map object, new scene: reuses the device allocations when the new map fits. */
 fdcm_status fdcm_dt3_rebuild(fdcm_dt3* map, const float* scene_xyxy, int32_t n_lines);
+/* fdcm_dt3_rebuild without the final wait: returns once the build kernels are queued (stream-ordered before any
+ * later call on this map); lets host-side preparation of the following search overlap the device build. */
+fdcm_status fdcm_dt3_rebuild_async(fdcm_dt3* map, const float* scene_xyxy, int32_t n_lines);
 /* Re-run the build kernels on the scene lines already resident on the device (kernel-only timing). */
 fdcm_status fdcm_dt3_rerun(fdcm_dt3* map);
 fdcm_status fdcm_dt3_retain(fdcm_dt3* map);

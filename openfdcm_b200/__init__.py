@@ -135,9 +135,9 @@ class Dt3Cuda:
         check(lib().fdcm_dt3_device_ptr(self._h, C.byref(p), C.byref(n)))
         return p.value, n.value
 
-    def rebuild(self, scene):
+    def rebuild(self, scene, wait=True):
         r = _records(scene)
-        check(lib().fdcm_dt3_rebuild(self._h, ptr(r), r.shape[0]))
+        check((lib().fdcm_dt3_rebuild if wait else lib().fdcm_dt3_rebuild_async)(self._h, ptr(r), r.shape[0]))
         self._refresh()
 
     def rerun(self):

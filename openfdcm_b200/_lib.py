@@ -46,6 +46,7 @@ SIGNATURES = {
     "fdcm_set_stream": (C.c_int, [C.c_int32, _P]),
     "fdcm_dt3_build": (C.c_int, [_P, C.c_int32, C.POINTER(Dt3Params), C.c_int32, C.c_int32, C.POINTER(_P)]),
     "fdcm_dt3_rebuild": (C.c_int, [_P, _P, C.c_int32]),
+    "fdcm_dt3_rebuild_async": (C.c_int, [_P, _P, C.c_int32]),
     "fdcm_dt3_rerun": (C.c_int, [_P]),
     "fdcm_dt3_retain": (C.c_int, [_P]),
     "fdcm_dt3_release": (C.c_int, [_P]),

@@ -498,7 +498,7 @@ extern "C" fdcm_status fdcm_dt3_build(const float* scene_xyxy, int32_t n_lines, 
     return FDCM_OK;
 }
 
-extern "C" fdcm_status fdcm_dt3_rebuild(fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines) {
+static fdcm_status rebuild_impl(fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines, bool wait) {
     if (!m) return fail(FDCM_ERR_INVALID, "map is null");
     if (n_lines < 0 || (n_lines > 0 && !scene_xyxy)) return fail(FDCM_ERR_INVALID, "bad scene");
     CUDA_TRY(cudaSetDevice(m->device));
@@ -506,12 +506,23 @@ extern "C" fdcm_status fdcm_dt3_rebuild(fdcm_dt3* m, const float* scene_xyxy, in
     if (fdcm_status st = get_stream(m->device, &s)) return st;
     fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
     if (st == FDCM_OK) st = run_build_kernels(m, s);
-    if (st == FDCM_OK) {
+    if (st == FDCM_OK && wait) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("rebuild: ") + cudaGetErrorString(e));
+        prof_resolve();
     }
-    prof_resolve();
     return st;
+}
+
+extern "C" fdcm_status fdcm_dt3_rebuild(fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines) {
+    return rebuild_impl(m, scene_xyxy, n_lines, true);
+}
+
+// Same as fdcm_dt3_rebuild but returns as soon as the build kernels are queued on the library stream: the host can
+// prepare the next call (e.g. the template ordering of fdcm_search_host) while the device builds the map.  Every later
+// call on this map is stream-ordered after the build; errors of the build surface at the next synchronising call.
+extern "C" fdcm_status fdcm_dt3_rebuild_async(fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines) {
+    return rebuild_impl(m, scene_xyxy, n_lines, false);
 }
 
 extern "C" fdcm_status fdcm_dt3_rerun(fdcm_dt3* m) {

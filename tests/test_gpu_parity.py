@@ -352,7 +352,7 @@ def test_config5_shape_multiview_batch():
     fm = fdcm.build_cuda_featuremap(scenes[0], fdcm.Dt3CudaParameters(30, 5.0, 1.5))
     for s, scene in enumerate(scenes):
         if s:
-            fm.rebuild(scene)
+            fm.rebuild(scene, wait=(s % 2 == 0))   # odd scenes: asynchronous rebuild, the search is stream-ordered after it
         top = fdcm.search_topk(fm, tset, None, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
         c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
         pen = orc.penalize(1, 1.5, c.search(tmpls, scene, 4, 4, batch=10), orc.template_lengths(tmpls))
