@@ -202,7 +202,8 @@ struct fdcm_dt3 {
     SlopeTableDev table_dev{};
     PropParams prop{};
     IntegralParams integ{};
-    DevBuf planes, mask, g, stack, lines, bins, rtab;
+    DevBuf planes, mask, g, stack, lines, bins, rtab, band_info, band_spill;
+    int row_mode = 0;           // exact-regime row pass: 0 = band kernel (default), 1 = literal, 2 = warp-per-row interval refinement
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
     mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
@@ -326,6 +327,8 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     {
         const char* e = std::getenv("FDCM_ROW_LITERAL");
         m->row_literal = e && e[0] == '1';
+        const char* e2 = std::getenv("FDCM_ROW_MODE");   // A/B testing of the exact-regime row kernels
+        m->row_mode = m->row_literal ? 1 : (e2 ? std::atoi(e2) : 0);
     }
 
     // translated scene (core/math.h:352-354) and orientation bins with the host libm (dt3cpu.h:123-134)
@@ -374,8 +377,13 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     const size_t n_px = (size_t)D * dm.plane_elems;
     CUDA_TRY(m->planes.reserve(n_px * sizeof(float)));
     CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t)));
-    if (m->exact) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
-    if (m->params.distance != FDCM_L1) CUDA_TRY(m->stack.reserve(n_px * 8));
+    const bool band_path = m->exact && m->params.distance != FDCM_L1 && m->row_mode == 0;
+    if (m->exact && !band_path) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
+    if (band_path) {
+        CUDA_TRY(m->band_info.reserve(dt_band_info_bytes(dm)));
+        CUDA_TRY(m->band_spill.reserve(dt_band_spill_bytes(dm, m->col_hi - m->col_lo + 1)));
+    }
+    if (m->params.distance != FDCM_L1 && !band_path) CUDA_TRY(m->stack.reserve(n_px * 8));
     CUDA_TRY(m->rtab.reserve((size_t)D * std::max(dm.W, dm.H) * sizeof(int32_t)));
     CUDA_TRY(m->lines.reserve((size_t)n_lines * 16));
     CUDA_TRY(m->bins.reserve((size_t)n_lines * 4));
@@ -403,7 +411,18 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
         launch_raster(m->lines.as<float>(), m->bins.as<int32_t>(), m->n_lines, dm, m->mask.as<uint32_t>(), s);
     }
     const int dist = m->params.distance;
-    if (m->exact) {
+    if (m->exact && dist != FDCM_L1 && m->row_mode == 0) {
+        {
+            KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
+            launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, s);
+        }
+        {
+            KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
+            launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+        }
+        KernelScope k("dt_row_fill", N, s);
+        launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+    } else if (m->exact) {
         {
             KernelScope k("dt_col_exact", N / 2, s);
             launch_dt_col_exact(m->mask.as<uint32_t>(), dm, m->g.as<uint16_t>(), s);
@@ -411,7 +430,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
         if (dist == FDCM_L1) {
             KernelScope k("dt_row_l1", N / 2 + N, s);
             launch_dt_row_l1(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
-        } else if (m->row_literal) {
+        } else if (m->row_mode == 1) {
             KernelScope k("dt_row_literal", N / 2 + N, s);
             launch_dt_pass_literal(true, true, m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->stack.p, s);
         } else {
@@ -1250,13 +1269,17 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
     DevBuf dg, dp, ds;
     cudaError_t e = dg.reserve(dm.plane_elems * 2);
     if (e == cudaSuccess) e = dp.reserve(dm.plane_elems * 4);
-    if (e == cudaSuccess) e = ds.reserve(dm.plane_elems * 8);
+    if (e == cudaSuccess) e = ds.reserve(literal == 2 ? dt_band_spill_bytes(dm, dm.W) : dm.plane_elems * 8);
     // same stream as the kernel: legacy-stream copies do not order against a non-blocking stream
     if (e == cudaSuccess) e = cudaMemsetAsync(dg.p, 0xFF, dm.plane_elems * 2, s);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(dg.p, (size_t)dm.pitch * 2, g_rows, (size_t)n * 2, (size_t)n * 2, n_rows, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
-        KernelScope k(literal ? "dt_row_literal" : "dt_row_exact", 0.0, s);
-        if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
+        KernelScope k(literal == 2 ? "dt_row_band" : (literal ? "dt_row_literal" : "dt_row_exact"), 0.0, s);
+        if (literal == 2) {
+            launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, s);
+            launch_dt_row_fill(dp.as<float>(), dm, ds.p, 0, dm.W - 1, s);
+        }
+        else if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
         else launch_dt_row_exact(dg.as<uint16_t>(), dp.as<float>(), dm, 0, dm.W - 1, s);
     }
     if (e == cudaSuccess) e = cudaGetLastError();

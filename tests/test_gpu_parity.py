@@ -241,14 +241,16 @@ def test_row_pass_exact_kernel_vs_literal_oracle(n):
             r = np.repeat(r[:: 8], 8)[:n] if n >= 8 else r      # plateaus
         rows.append(r)
     g = np.stack([np.asarray(r).astype(np.int64)[:n] for r in rows]).astype(np.uint16)
-    got = _dt_rows(g, literal=False)
-    lit = _dt_rows(g, literal=True)
+    got = _dt_rows(g, literal=0)
+    lit = _dt_rows(g, literal=1)
+    band = _dt_rows(g, literal=2)   # lane-per-row band kernel (the product path), g given explicitly
     fmax = np.finfo(np.float32).max
     for i in range(g.shape[0]):
         f = np.where(g[i] == big, fmax, g[i].astype(np.float64) ** 2).astype(F32)
         want = orc.dt_pass_l2_1d(f)
         assert np.array_equal(lit[i], want), f"literal kernel row {i}"
         assert np.array_equal(got[i], want), f"exact kernel row {i}: first diff at {np.flatnonzero(got[i] != want)[:5]}"
+        assert np.array_equal(band[i], want), f"band kernel row {i}: first diff at {np.flatnonzero(band[i] != want)[:5]}"
 
 
 @pytest.mark.parametrize("batch", [10, 0], ids=["BatchOptimize(10)", "DefaultOptimize"])
