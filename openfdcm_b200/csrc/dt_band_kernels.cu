@@ -83,48 +83,87 @@ __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __rest
 // row call, one lane per row
 // =============================================================================================
 constexpr int kRing = 32;                       // stack entries below the top kept in shared memory, per row
-constexpr int kTileP = 33;                      // pitch of the 32x32 output transposition tile
 constexpr int kBandWarps = 2;                   // warps (= bands) per CTA
 
-// stack entry: x = f(v) + v^2 during the envelope build, then the chained base value of the vertex;
-//              y = v | (first owned pixel) << 16
+// stack entry: x = f(v) + v^2, y = v | (first owned pixel) << 16
+__device__ __forceinline__ void sts_u64(uint32_t addr, uint2 v) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ uint2 lds_u64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// The envelope stack of one row: top entry in registers, the kRing entries below it in a shared-memory ring (this
+// lane's column of [kRing][32] 8-byte slots), older ones in the row's global array (a sequential walk stays inside
+// one 128-byte line for 16 entries, so only one access in 16 pays the L2 latency).
 struct RowStack {
-    uint2* ring;            // shared: [kRing][32], this lane's column at + lane
-    uint2* spill;           // global: this row's own [maxdepth] array (sequential walks stay inside a 128-byte line for
-                            // 16 entries, so only one access in 16 pays the L2 latency)
-    int k, lo;              // index of the top entry (registers); the ring holds entries [lo, k-1]
-    uint32_t topkey;
+    uint32_t ring0;         // shared address of this lane's slot 0
+    uint32_t so;            // byte offset of slot (k & (kRing-1)): where entry k goes when it is displaced from the registers
+    uint2* spill;
+    int k, cnt;             // index of the top entry; the ring holds entries [k - cnt, k - 1]
+    uint32_t topkey, topvs;
     int topv, tops;
     __device__ __forceinline__ void push(int v, int start, uint32_t key) {
         if (k >= 0) {
-            const int slot = (k & (kRing - 1)) * 32;
-            if (k - lo == kRing) {               // ring full: its oldest entry (same slot) moves to global memory
-                spill[lo] = ring[slot];
-                ++lo;
-            }
-            ring[slot] = make_uint2(topkey, (uint32_t)topv | ((uint32_t)tops << 16));
+            if (cnt == kRing) spill[k - kRing] = lds_u64(ring0 + so);   // ring full: its oldest entry (same slot) leaves
+            else ++cnt;
+            sts_u64(ring0 + so, make_uint2(topkey, topvs));
         }
         ++k;
+        so = (so + 256u) & (kRing * 256u - 1u);
         topv = v; tops = start; topkey = key;
+        topvs = (uint32_t)v | ((uint32_t)start << 16);
     }
     __device__ __forceinline__ void pop() {
         --k;
+        so = (so - 256u) & (kRing * 256u - 1u);
         if (k < 0) return;
         uint2 e;
-        if (k >= lo) {
-            e = ring[(k & (kRing - 1)) * 32];
-        } else {                                 // ring empty: fetch from the spilled part
+        if (cnt > 0) {
+            --cnt;
+            e = lds_u64(ring0 + so);
+        } else {
             e = spill[k];
-            lo = k;
         }
         topkey = e.x;
+        topvs = e.y;
         topv = (int)(e.y & 0xFFFFu);
         tops = (int)(e.y >> 16);
+    }
+    // one column: parabola (v, key = g^2 + v^2) against the envelope so far (imgproc.h:104-120 on integers)
+    __device__ __forceinline__ void column(int v, int gv, int Wm1) {
+        const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
+        int start = 0;
+        while (k >= 0) {
+            // v beats the top strictly from pixel floor(N / Dn) + 1 on (the left parabola keeps ties)
+            const int N = (int)key - (int)topkey;
+            const int Dn = 2 * (v - topv);
+            if (N < tops * Dn) {                 // ... not after the top's first pixel: the top owns nothing
+                pop();
+                continue;
+            }
+            if (N >= Wm1 * Dn) return;           // ... beyond the last pixel of the row: v never owns anything
+            // 0 <= N / Dn < W - 1 <= 2896: the biased approximate quotient is below the true one by less than 0.003
+            const float qf = __fmaf_rn((float)N, rcp_approx((float)Dn), -0.002f);
+            const int t = __float2int_rd(qf);    // floor(N / Dn) or one less
+            start = t + 1 + ((N - t * Dn) >= Dn ? 1 : 0);
+            break;
+        }
+        push(v, start, key);
     }
 };
 
 // kFromG = false: g is derived from the band records of dt_col_band_kernel (product path).
 // kFromG = true : g rows are given explicitly (u16, 0xFFFF = FLT_MAX), any content (row-pass parity tests).
+// Workspace rows are padded to 32 per band (row id = (d * nbands + b) * 32 + lane) so that the rows past H of the last
+// band need no special case: they build an envelope nobody reads.
 template <bool kFromG>
 __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint2* __restrict__ info,
                                                                       const uint16_t* __restrict__ g, MapDims dm, int nbands,
@@ -136,20 +175,24 @@ __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint
     if (wg >= dm.D * nbands) return;
     const int d = wg % dm.D, b = wg / dm.D;
     const int row0 = b * 32;
-    const int W = dm.W;
-    const uint2* info_row = info + ((size_t)d * nbands + b) * dm.pitch;
+    const int W = dm.W, Wm1 = dm.W - 1;
+    const uint2* info_row = info + ((size_t)d * nbands + b) * dm.pitch + lane;
     const uint16_t* g_row = kFromG ? g + ((size_t)d * dm.H + min(row0 + lane, dm.H - 1)) * dm.pitch : nullptr;
-    const bool row_ok = row0 + lane < dm.H;
+    const size_t prow = ((size_t)d * nbands + b) * 32 + lane;
 
     RowStack st;
-    st.ring = ring_all[warp] + lane;
-    st.spill = spill_all + ((size_t)d * dm.H + min(row0 + lane, dm.H - 1)) * maxdepth;   // rows >= H never push
-    st.k = -1; st.lo = 0; st.topkey = 0; st.topv = 0; st.tops = 0;
+    st.ring0 = (uint32_t)__cvta_generic_to_shared(ring_all[warp]) + (uint32_t)lane * 8u;
+    st.so = (kRing - 1) * 256u;
+    st.spill = spill_all + prow * maxdepth;
+    st.k = -1; st.cnt = 0; st.topkey = 0; st.topvs = 0; st.topv = 0; st.tops = 0;
     const uint32_t mle = 0xFFFFFFFFu >> (31 - lane), mge = 0xFFFFFFFFu << lane;
+    const int l31 = 31 - lane;
 
     // ---- lower envelope over the columns that hold a finite g (imgproc.h:101-121) ----
+    uint2 e_next = make_uint2(0u, 0xFFFFFFFFu);
+    if (!kFromG && lane < W) e_next = info_row[0];
     for (int x0 = 0; x0 < dm.pitch; x0 += 32) {
-        uint2 e = make_uint2(0u, 0xFFFFFFFFu);
+        const uint2 e = e_next;
         unsigned todo;
         if (kFromG) {
             // lane = column here: which of the 32 columns hold a finite value in ANY row of the band
@@ -158,55 +201,46 @@ __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint
                 if (g[((size_t)d * dm.H + row0 + r) * dm.pitch + x0 + lane] != kNone16) any = 1;
             todo = __ballot_sync(0xffffffffu, any && x0 + lane < W);
         } else {
-            if (x0 + lane < W) e = info_row[x0 + lane];
+            e_next = make_uint2(0u, 0xFFFFFFFFu);
+            if (x0 + 32 + lane < W) e_next = info_row[x0 + 32];           // next chunk's records, one iteration ahead
             todo = __ballot_sync(0xffffffffu, e.x != 0u || e.y != 0xFFFFFFFFu);
         }
-        while (todo) {
-            const int j = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int v = x0 + j;
-            int gv;
-            bool fin = row_ok;
-            if (kFromG) {
-                gv = g_row[v];
-                fin = row_ok && gv != (int)kNone16;
-            } else {
+        if (kFromG) {
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int gv = g_row[x0 + j];
+                if (row0 + lane < dm.H && gv != (int)kNone16) st.column(x0 + j, gv, Wm1);
+            }
+        } else if (__ballot_sync(0xffffffffu, e.x != 0u) == 0u) {
+            // no edge pixel inside the band in these 32 columns: g = distance to the nearest edge above / below the band
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const uint32_t ud = __shfl_sync(0xffffffffu, e.y, j);
+                const int gv = min(lane + (int)(ud & 0xFFFFu), l31 + (int)(ud >> 16));
+                st.column(x0 + j, gv, Wm1);
+            }
+        } else {
+            while (todo) {
+                const int j = __ffs(todo) - 1;
+                todo &= todo - 1;
                 const uint32_t M = __shfl_sync(0xffffffffu, e.x, j), ud = __shfl_sync(0xffffffffu, e.y, j);
                 const uint32_t above = M & mle, below = M & mge;
-                const int upd = above ? (lane - (31 - __clz(above))) : (lane + (int)(ud & 0xFFFFu));
-                const int dnd = below ? (__ffs(below) - 1 - lane) : (31 - lane + (int)(ud >> 16));
-                gv = min(upd, dnd);
-            }
-            if (fin) {
-                const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
-                int start = 0;
-                while (st.k >= 0) {
-                    // parabola v beats the top strictly from pixel floor(N / Dn) + 1 on (left one keeps ties)
-                    const int N = (int)key - (int)st.topkey;
-                    const int Dn = 2 * (v - st.topv);
-                    if (N < st.tops * Dn) {      // ... which is not after the top's first pixel: the top owns nothing
-                        st.pop();
-                        continue;
-                    }
-                    const float qf = __fdividef((float)N, (float)Dn);
-                    if (qf >= 4096.f) { start = 0x7FFF; break; }   // far beyond the row (W <= 2897): never an owner
-                    int t = (int)qf;
-                    const int r = N - t * Dn;
-                    if (r < 0) --t; else if (r >= Dn) ++t;
-                    start = t + 1;
-                    break;
-                }
-                if (start < W) st.push(v, start, key);
+                const int ua = __clz(above) - 31, ub = (int)(ud & 0xFFFFu);       // lane - (row of the last edge at or above)
+                const int da = __ffs(below) - 1 - 31, db = (int)(ud >> 16);       // (row of the first edge at or below) - 31
+                const int gv = min(lane + (above ? ua : ub), l31 + (below ? da : db));
+                st.column(x0 + j, gv, Wm1);
             }
         }
     }
     // ---- park the whole stack in the row's global array; the fill kernel walks it ----
     const int K = st.k + 1;
     if (K > 0) {
-        for (int i = st.lo; i < st.k; ++i) st.spill[i] = st.ring[(i & (kRing - 1)) * 32];
-        st.spill[st.k] = make_uint2(st.topkey, (uint32_t)st.topv | ((uint32_t)st.tops << 16));
+        for (int i = st.k - st.cnt; i < st.k; ++i) st.spill[i] = lds_u64(st.ring0 + (uint32_t)(i & (kRing - 1)) * 256u);
+        st.spill[st.k] = make_uint2(st.topkey, st.topvs);
     }
-    if (row_ok) row_k[(size_t)d * dm.H + row0 + lane] = K;
+    row_k[prow] = K;
 }
 
 // =============================================================================================
@@ -220,6 +254,14 @@ __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint
 // =============================================================================================
 constexpr int kFillWarps = 4;
 
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
+// [win_lo, win_lo + win_w): columns that can hold envelope vertices, both multiples of 32
 __global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint2* __restrict__ spill_all,
                                                                       const int32_t* __restrict__ row_k,
                                                                       float* __restrict__ planes, MapDims dm, int n_rows_total,
@@ -228,88 +270,95 @@ __global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kFillWarps + warp;           // row of the [D*H][pitch] stack of planes
     if (row >= n_rows_total) return;
-    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)warp * win_w - win_lo;   // indexed by absolute column
+    // shared-memory copy of the row's window, addressed by absolute column: rb0 + 4 * q
+    const uint32_t rb0 = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)(warp * win_w - win_lo) * 4u;
     const int W = dm.W;
-    float* orow = planes + (size_t)row * dm.pitch;
-    const int K = row_k[row];
+    float* op = planes + (size_t)row * dm.pitch + lane;       // this lane's pixel of the current chunk
+    const size_t prow = (size_t)(row / dm.H) * (size_t)(((dm.H + 31) >> 5) << 5) + (size_t)(row % dm.H);   // padded workspace row
+    const int K = row_k[prow];
     if (K <= 0) {                                             // no edge pixel in this plane: FLT_MAX stays (imgproc.h:174)
-        for (int q = lane; q < W; q += 32) orow[q] = FLT_MAX;
+        for (int q = lane; q < W; q += 32, op += 32) *op = FLT_MAX;
         return;
     }
-    const uint2* sp = spill_all + (size_t)row * maxdepth;
+    const uint2* sp = spill_all + prow * maxdepth + lane;
     const uint2 kSentinel = make_uint2(0u, 0xFFFFFFFFu);      // s = 0xFFFF: never starts inside a chunk
-    uint2 be = lane < K ? sp[lane] : kSentinel;
-    uint2 nbe = 32 + lane < K ? sp[32 + lane] : kSentinel;
-    int e0 = 0;
+    uint2 be = lane < K ? sp[0] : kSentinel;
+    uint2 nbe = 32 + lane < K ? sp[32] : kSentinel;
+    int e0 = 0;                                               // the batch holds entries [e0, e0 + 32), one per lane
     int bv = (int)(be.y & 0xFFFFu), bs = (int)(be.y >> 16);
     uint32_t bf = be.x - (uint32_t)(bv * bv);
     int carry_v = __shfl_sync(0xffffffffu, bv, 0);            // entry 0: s = 0 <= v
     uint32_t carry_b = __shfl_sync(0xffffffffu, bf, 0);
+    int ci = 0;                                               // entries consumed so far (uniform)
+    int nxt = 0;                                              // first pixel of the first unconsumed entry (uniform)
     const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
-    for (int q0 = 0; q0 < dm.pitch; q0 += 32) {
+    const int win_hi = win_lo + win_w;
+    for (int q0 = 0; q0 < dm.pitch; q0 += 32, op += 32) {
         const int q = q0 + lane;
         int ov = carry_v;
         uint32_t ob = carry_b;
-        while (true) {
-            const int rel = bs - q0;
-            const bool inb = (unsigned)rel < 32u;
-            const unsigned marks = __reduce_or_sync(0xffffffffu, inb ? (1u << rel) : 0u);
-            if (marks) {
-                const unsigned bal = __ballot_sync(0xffffffffu, inb);
-                const int first = __ffs(bal) - 1;
-                const bool chain = inb && bs > bv;
-                bool ready = !chain;
-                uint32_t base = bf;
-                if (chain && bv < q0) {
-                    base = rowbuf[bv];
-                    ready = true;
-                }
-                const int c = __popc(marks & le_mask);
-                const int src = (first + c - 1) & 31;
-                unsigned pend = __ballot_sync(0xffffffffu, inb && !ready);
-                int pv;
-                uint32_t pb;
-                while (true) {
-                    const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
-                    const int sv = __shfl_sync(0xffffffffu, bv, src);
-                    pv = c ? sv : ov;
-                    pb = c ? sb : ob;
-                    if (!pend) break;
-                    const int dq = q - pv;
-                    const uint32_t val = pb + (uint32_t)(dq * dq);
-                    const bool pok = c == 0 || !((pend >> src) & 1u);       // this pixel's owner already has its base
-                    const int pix = (bv - q0) & 31;
-                    const uint32_t vv = __shfl_sync(0xffffffffu, val, pix);
-                    const unsigned okb = __ballot_sync(0xffffffffu, pok);
-                    if (inb && !ready && ((okb >> pix) & 1u)) {
-                        base = vv;
-                        ready = true;
-                    }
-                    pend = __ballot_sync(0xffffffffu, inb && !ready);
-                }
-                ov = pv;
-                ob = pb;
-                const int lastl = 31 - __clz(bal);
-                carry_v = __shfl_sync(0xffffffffu, bv, lastl);
-                carry_b = __shfl_sync(0xffffffffu, base, lastl);
-            }
-            const int last_s = __shfl_sync(0xffffffffu, bs, 31);
-            if (last_s < q0 + 32 && e0 + 32 < K) {            // the chunk continues in the next 32 entries
+        while (nxt < q0 + 32) {                               // some interval starts inside this chunk
+            if (ci == e0 + 32) {                              // ... in the next 32 entries
                 e0 += 32;
                 be = nbe;
-                nbe = e0 + 32 + lane < K ? sp[e0 + 32 + lane] : kSentinel;
+                nbe = e0 + 32 + lane < K ? sp[e0 + 32] : kSentinel;
                 bv = (int)(be.y & 0xFFFFu);
                 bs = (int)(be.y >> 16);
                 bf = be.x - (uint32_t)(bv * bv);
-                continue;
             }
-            break;
+            const int rel = bs - q0;
+            const bool inb = (unsigned)rel < 32u;             // consecutive lanes starting at ci - e0 (s is increasing)
+            const unsigned bal = __ballot_sync(0xffffffffu, inb);
+            const unsigned marks = __reduce_or_sync(0xffffffffu, inb ? (1u << rel) : 0u);
+            const int first = ci - e0;
+            const bool chain = inb && bs > bv;
+            bool ready = !chain;
+            uint32_t base = bf;
+            const bool from_row = chain && bv < q0;
+            if (__any_sync(0xffffffffu, from_row)) {
+                __syncwarp();                                 // orders the earlier chunks' st.shared before this read
+                if (from_row) {
+                    base = lds_u32(rb0 + 4u * (uint32_t)bv);
+                    ready = true;
+                }
+            }
+            const int c = __popc(marks & le_mask);
+            const int src = (first + c - 1) & 31;
+            unsigned pend = __ballot_sync(0xffffffffu, inb && !ready);
+            int pv;
+            uint32_t pb;
+            while (true) {
+                const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
+                const int sv = __shfl_sync(0xffffffffu, bv, src);
+                pv = c ? sv : ov;
+                pb = c ? sb : ob;
+                if (!pend) break;
+                const int dq = q - pv;
+                const uint32_t val = pb + (uint32_t)(dq * dq);
+                const bool pok = c == 0 || !((pend >> src) & 1u);       // this pixel's owner already has its base
+                const int pix = (bv - q0) & 31;
+                const uint32_t vv = __shfl_sync(0xffffffffu, val, pix);
+                const unsigned okb = __ballot_sync(0xffffffffu, pok);
+                if (inb && !ready && ((okb >> pix) & 1u)) {
+                    base = vv;
+                    ready = true;
+                }
+                pend = __ballot_sync(0xffffffffu, inb && !ready);
+            }
+            ov = pv;
+            ob = pb;
+            const int lastl = 31 - __clz(bal);
+            carry_v = __shfl_sync(0xffffffffu, bv, lastl);
+            carry_b = __shfl_sync(0xffffffffu, base, lastl);
+            ci += __popc(bal);
+            if (ci >= K) nxt = 0x7FFFFFFF;
+            else if (ci < e0 + 32) nxt = __shfl_sync(0xffffffffu, bs, ci - e0);
+            else nxt = (int)(__shfl_sync(0xffffffffu, nbe.y, 0) >> 16);
         }
         const int dq = q - ov;
         const uint32_t val = ob + (uint32_t)(dq * dq);
-        if (q >= win_lo && q < win_lo + win_w) rowbuf[q] = val;
-        if (q < W) orow[q] = (float)val;                      // < 2^24: exact
-        __syncwarp();
+        if (q0 >= win_lo && q0 < win_hi) sts_u32(rb0 + 4u * (uint32_t)q, val);
+        if (q < W) *op = (float)val;                          // < 2^24: exact
     }
 }
 
@@ -317,10 +366,11 @@ static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1
 
 int dt_band_count(const MapDims& dm) { return (dm.H + 31) / 32; }
 size_t dt_band_info_bytes(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * dm.pitch * sizeof(uint2); }
-static size_t row_k_bytes(const MapDims& dm) { return ((size_t)dm.D * dm.H * sizeof(int32_t) + 255) / 256 * 256; }
+static size_t padded_rows(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * 32; }
+static size_t row_k_bytes(const MapDims& dm) { return (padded_rows(dm) * sizeof(int32_t) + 255) / 256 * 256; }
 // workspace of the row call: per-row envelope length + per-row envelope array of maxdepth entries
 size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth) {
-    return row_k_bytes(dm) + (size_t)dm.D * dm.H * (size_t)maxdepth * sizeof(uint2);
+    return row_k_bytes(dm) + padded_rows(dm) * (size_t)maxdepth * sizeof(uint2);
 }
 
 void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, cudaStream_t s) {
@@ -355,14 +405,16 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int rows = dm.D * dm.H;
-    const size_t smem = (size_t)kFillWarps * ws.maxdepth * sizeof(uint32_t);
+    const int wl = ws.win_lo & ~31;
+    const int ww = ((ws.win_lo + ws.maxdepth + 31) & ~31) - wl;
+    const size_t smem = (size_t)kFillWarps * ww * sizeof(uint32_t);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(dt_row_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
         attr_set = true;
     }
     dt_row_fill_kernel<<<cdiv_u(rows, kFillWarps), kFillWarps * 32, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, rows, ws.maxdepth,
-                                                                              ws.win_lo, ws.maxdepth);
+                                                                              wl, ww);
 }
 
 }   // namespace fdcm
