@@ -847,8 +847,17 @@ __global__ void integral_shift_table_kernel(int32_t* __restrict__ rtab, int len,
     rtab[(size_t)d * len + i] = (int32_t)round_to_ll((float)i * r);
 }
 
-// y-major planes: thread per chain, the row access of a warp is one coalesced 128-byte segment; 16 loads in
+__device__ __forceinline__ void cp_async_f32(uint32_t smem_addr, const float* gptr) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// y-major planes: thread per chain, the row access of a warp is one coalesced 128-byte segment; kYU loads in
 // flight per thread hide the HBM latency (the running sum itself is the only serial dependency).
+constexpr int kYU = 32;
+
 __global__ void __launch_bounds__(128) integral_ymajor_kernel(float* __restrict__ planes, MapDims dm,
                                                               const __grid_constant__ IntegralParams ip,
                                                               const int32_t* __restrict__ rtab, int rlen) {
@@ -859,50 +868,55 @@ __global__ void __launch_bounds__(128) integral_ymajor_kernel(float* __restrict_
     const int Rend = R[dm.H - 1];
     const int cmin = Rend > 0 ? -Rend : 0;
     const int cmax = (Rend < 0 ? -Rend : 0) + dm.W - 1;
-    const int c = cmin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > cmax) return;
+    int c = cmin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (cmin + (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) > cmax) return;   // whole warp past the last chain
+    if (c > cmax) c = 0x20000000;                                                         // idle lane: every x is out of range
     // rows are visited at y = p0y + i*sy: fold the direction into a row pointer and a signed pitch
     const long long rstep = ry < 0 ? -(long long)dm.pitch : (long long)dm.pitch;
     float* row = planes + (size_t)d * dm.plane_elems + (ry < 0 ? (size_t)(dm.H - 1) * dm.pitch : 0);
     float acc = 0.f;
     bool have = false;
-    constexpr int U = 16;
-    for (int i0 = 0; i0 < dm.H; i0 += U) {
-        float a[U];
-        int xs[U];
+    for (int i0 = 0; i0 < dm.H; i0 += kYU) {
+        float a[kYU];
+        const int32_t rl = (i0 + (int)(threadIdx.x & 31) < dm.H) ? __ldg(R + i0 + (threadIdx.x & 31)) : 0x40000000;   // lane k: shift of row i0+k
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            const int i = i0 + k;
-            const int x = (i < dm.H) ? c + __ldg(R + i) : -1;
-            xs[k] = ((unsigned)x < (unsigned)dm.W) ? x : -1;
-            a[k] = xs[k] >= 0 ? row[(long long)k * rstep + xs[k]] : 0.f;
+        for (int k = 0; k < kYU; ++k) {
+            const int x = c + __shfl_sync(0xffffffffu, rl, k);
+            a[k] = ((unsigned)x < (unsigned)dm.W) ? row[(long long)k * rstep + x] : 0.f;
         }
 #pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (xs[k] >= 0) {
-                if (have) { acc = a[k] + acc; row[(long long)k * rstep + xs[k]] = acc; }
+        for (int k = 0; k < kYU; ++k) {
+            const int x = c + __shfl_sync(0xffffffffu, rl, k);
+            if ((unsigned)x < (unsigned)dm.W) {
+                if (have) { acc = a[k] + acc; row[(long long)k * rstep + x] = acc; }
                 else { acc = a[k]; have = true; }
             } else {
                 have = false;
             }
         }
-        row += (long long)U * rstep;
+        row += (long long)kYU * rstep;
     }
 }
 
 // x-major planes: a warp owns 32 consecutive chains and walks the columns in blocks of 32.  Each block is
 // staged through a shared-memory tile (<= 64 rows x 32 columns, row segments loaded / stored as coalesced
-// 128-byte pieces), lane j then runs chain j sequentially across the 32 columns of the tile.
+// 128-byte pieces), lane j then runs chain j sequentially across the 32 columns of the tile.  Tiles are double
+// buffered with cp.async: the next tile's rows are in flight while the current one is summed and written back.
 constexpr int kTileRows = 64, kTilePitch = 33;
+
+struct XTile {              // geometry of one 32-column block for one warp
+    int ybase, r_lo, r_hi, off, ncols;
+};
 
 __global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict__ planes, MapDims dm,
                                                               const __grid_constant__ IntegralParams ip,
                                                               const int32_t* __restrict__ rtab, int rlen) {
-    __shared__ float tiles[4][kTileRows * kTilePitch];
+    extern __shared__ __align__(16) float tiles_all[];       // [4 warps][2 buffers][kTileRows * kTilePitch]
     const int d = blockIdx.y;
     if (ip.mode[d] != 1) return;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile = tiles[warp];
+    float* tile0 = tiles_all + (size_t)warp * 2 * kTileRows * kTilePitch;
+    const uint32_t tile0_s = (uint32_t)__cvta_generic_to_shared(tile0);
     float* P = planes + (size_t)d * dm.plane_elems;
     const int32_t* R = rtab + (size_t)d * rlen;
     const float rx = ip.rx[d];
@@ -913,32 +927,50 @@ __global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict_
     const int cmax = (Rend < 0 ? -Rend : 0) + dm.H - 1;
     const int c0 = cmin + (blockIdx.x * 4 + warp) * 32;                    // first chain of this warp
     if (c0 > cmax) return;
-    float acc = 0.f;
-    bool have = false;
-    for (int i0 = 0; i0 < dm.W; i0 += 32) {
+    auto geometry = [&](int i0) {
+        XTile g;
         const int i = i0 + lane;                                           // this lane's column step (load/store role)
         const bool col_ok = i < dm.W;
         const int Rl = R[col_ok ? i : dm.W - 1];
         const int Ra = __shfl_sync(0xffffffffu, Rl, 0);
         const int Rb = __shfl_sync(0xffffffffu, Rl, min(31, dm.W - 1 - i0));
         const int Rmin = min(Ra, Rb);
-        const int ybase = c0 + Rmin;
+        g.ybase = c0 + Rmin;
         const int nrows = 32 + abs(Ra - Rb);
-        const int r_lo = max(0, -ybase), r_hi = min(nrows, dm.H - ybase);  // rows of the tile inside the image
-        const int off = col_ok ? Rl - Rmin : 0x40000000;                   // tile row of chain c0 in this lane's column
-        float* gp = P + (long long)(ybase + r_lo) * dm.pitch + (p0x + i * sx);
-        // ---- load: row r of the tile, lane = column; element belongs to chain (r - off) ----
-        for (int r = r_lo; r < r_hi; ++r, gp += dm.pitch)
-            if ((unsigned)(r - off) < 32u) tile[r * kTilePitch + lane] = *gp;
+        g.r_lo = max(0, -g.ybase);                                         // rows of the tile inside the image
+        g.r_hi = min(nrows, dm.H - g.ybase);
+        g.off = col_ok ? Rl - Rmin : 0x40000000;                           // tile row of chain c0 in this lane's column
+        g.ncols = min(32, dm.W - i0);
+        return g;
+    };
+    // row r of the tile, lane = column; the element belongs to chain (r - off)
+    auto load = [&](int i0, int buf) {
+        if (i0 < dm.W) {
+            const XTile g = geometry(i0);
+            const float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (p0x + (i0 + lane) * sx);
+            uint32_t sp = tile0_s + (uint32_t)((buf * kTileRows + g.r_lo) * kTilePitch + lane) * 4u;
+            for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch, sp += kTilePitch * 4u)
+                if ((unsigned)(r - g.off) < 32u) cp_async_f32(sp, gp);
+        }
+        cp_async_commit();
+    };
+    float acc = 0.f;
+    bool have = false;
+    load(0, 0);
+    int buf = 0;
+    for (int i0 = 0; i0 < dm.W; i0 += 32, buf ^= 1) {
+        load(i0 + 32, buf ^ 1);
+        cp_async_wait<1>();
         __syncwarp();
+        float* tile = tile0 + (size_t)buf * kTileRows * kTilePitch;
+        const XTile g = geometry(i0);
         // ---- sequential sums: lane = chain; the 32 tile values of the chain go through registers ----
-        const int ncols = min(32, dm.W - i0);
         float v[32];
         int rr[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-            const int r = lane + __shfl_sync(0xffffffffu, off, j);         // tile row of this lane's chain in column j
-            rr[j] = (j < ncols && r >= r_lo && r < r_hi) ? r * kTilePitch + j : -1;
+            const int r = lane + __shfl_sync(0xffffffffu, g.off, j);       // tile row of this lane's chain in column j
+            rr[j] = (j < g.ncols && r >= g.r_lo && r < g.r_hi) ? r * kTilePitch + j : -1;
             v[j] = rr[j] >= 0 ? tile[rr[j]] : 0.f;
         }
 #pragma unroll
@@ -946,15 +978,15 @@ __global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict_
             if (rr[j] >= 0) {
                 if (have) { acc = v[j] + acc; tile[rr[j]] = acc; }
                 else { acc = v[j]; have = true; }
-            } else if (j < ncols) {
+            } else if (j < g.ncols) {
                 have = false;
             }
         }
         __syncwarp();
         // ---- store ----
-        gp = P + (long long)(ybase + r_lo) * dm.pitch + (p0x + i * sx);
-        for (int r = r_lo; r < r_hi; ++r, gp += dm.pitch)
-            if ((unsigned)(r - off) < 32u) *gp = tile[r * kTilePitch + lane];
+        float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (p0x + (i0 + lane) * sx);
+        for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch)
+            if ((unsigned)(r - g.off) < 32u) *gp = tile[r * kTilePitch + lane];
         __syncwarp();
     }
 }
@@ -1073,7 +1105,15 @@ void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& i
         any_y |= ip.mode[d] == 2;
     }
     if (any_y) integral_ymajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
-    if (any_x) integral_xmajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
+    if (any_x) {
+        const size_t smem = (size_t)4 * 2 * kTileRows * kTilePitch * sizeof(float);
+        static bool attr_set = false;
+        if (!attr_set) {
+            cudaFuncSetAttribute(integral_xmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set = true;
+        }
+        integral_xmajor_kernel<<<grid, 128, smem, s>>>(d_planes, dm, ip, d_rtab, rlen);
+    }
 }
 
 }   // namespace fdcm
