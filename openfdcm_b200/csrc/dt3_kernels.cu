@@ -9,6 +9,8 @@
 //   K4 integral_kernel          lineIntegral: sequential fp32 running sums along each plane's discrete lines
 // Layout: orientation-major [D][H][pitch] fp32, pitch % 32 == 0.
 // All float arithmetic is non-fused (-fmad=false) and ordered exactly as the reference's expressions.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -908,7 +910,7 @@ struct XTile {              // geometry of one 32-column block for one warp
     int ybase, r_lo, r_hi, off, ncols;
 };
 
-__global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict__ planes, MapDims dm,
+__global__ void __launch_bounds__(128) integral_xmajor_scalar_kernel(float* __restrict__ planes, MapDims dm,
                                                               const __grid_constant__ IntegralParams ip,
                                                               const int32_t* __restrict__ rtab, int rlen) {
     extern __shared__ __align__(16) float tiles_all[];       // [4 warps][2 buffers][kTileRows * kTilePitch]
@@ -987,6 +989,137 @@ __global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict_
         float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (p0x + (i0 + lane) * sx);
         for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch)
             if ((unsigned)(r - g.off) < 32u) *gp = tile[r * kTilePitch + lane];
+        __syncwarp();
+    }
+}
+
+// x-major planes, vector path (W % 4 == 0): the same tiles, but staged with 16-byte cp.async (LDGSTS.128 moves 512
+// bytes per warp instruction; the 4-byte form is limited to about one element per cycle per SM) as full row segments
+// in memory order (pitch kVecPitch floats, 16-byte aligned rows).  A column walk over 16-byte staged rows can only
+// reach the 8 banks congruent to the column (mod 4), so the four 8-lane groups of the warp run 0..3 columns behind
+// each other: bank = 4*(lane%8) + 4*shift + column - lane/8 is then distinct for all 32 lanes.
+constexpr int kVecPitch = 36;
+constexpr int kSkew = 3;
+
+__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const float* gptr) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+}
+
+__global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict__ planes, MapDims dm,
+                                                              const __grid_constant__ IntegralParams ip,
+                                                              const int32_t* __restrict__ rtab, int rlen) {
+    extern __shared__ __align__(16) float tiles_all[];       // [4 warps][2 buffers][kTileRows * kVecPitch]
+    const int d = blockIdx.y;
+    if (ip.mode[d] != 1) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* tile0 = tiles_all + (size_t)warp * 2 * kTileRows * kVecPitch;
+    const uint32_t tile0_s = (uint32_t)__cvta_generic_to_shared(tile0);
+    float* P = planes + (size_t)d * dm.plane_elems;
+    const int32_t* R = rtab + (size_t)d * rlen;
+    const bool fwd = !(ip.rx[d] < 0);                                      // column step i is x = i (fwd) or x = W-1-i
+    const int Rend = R[dm.W - 1];
+    const int cmin = Rend > 0 ? -Rend : 0;
+    const int cmax = (Rend < 0 ? -Rend : 0) + dm.H - 1;
+    const int c0 = cmin + (blockIdx.x * 4 + warp) * 32;                    // first chain of this warp
+    if (c0 > cmax) return;
+    const int grp = lane >> 3;                                             // this lane's lag in the column walk
+    auto geometry = [&](int i0) {
+        XTile g;
+        const int i = i0 + lane;                                           // this lane's column step (shift-table role)
+        const bool col_ok = i < dm.W;
+        const int Rl = R[col_ok ? i : dm.W - 1];
+        const int Ra = __shfl_sync(0xffffffffu, Rl, 0);
+        const int Rb = __shfl_sync(0xffffffffu, Rl, min(31, dm.W - 1 - i0));
+        const int Rmin = min(Ra, Rb);
+        g.ybase = c0 + Rmin;
+        const int nrows = 32 + abs(Ra - Rb);
+        g.r_lo = max(0, -g.ybase);                                         // rows of the tile inside the image
+        g.r_hi = min(nrows, dm.H - g.ybase);
+        g.off = col_ok ? Rl - Rmin : 0x40000000;                           // tile row of chain c0 at this lane's column step
+        g.ncols = min(32, dm.W - i0);
+        return g;
+    };
+    // memory column m of the tile <-> x = xbase + m; column step j sits at m = j (fwd) or 31 - j
+    auto load = [&](int i0, int buf) {
+        if (i0 < dm.W) {
+            const XTile g = geometry(i0);
+            const int xbase = fwd ? i0 : dm.W - 32 - i0;
+            const int x = xbase + 4 * (lane & 7);
+            const bool chunk_ok = x >= 0 && x + 3 < dm.W;
+            const int r0 = g.r_lo + (lane >> 3);
+            const float* gp = P + (long long)(g.ybase + r0) * dm.pitch + x;
+            uint32_t sp = tile0_s + (uint32_t)((buf * kTileRows + r0) * kVecPitch + 4 * (lane & 7)) * 4u;
+            for (int r = r0; r < g.r_hi; r += 4, gp += 4 * (long long)dm.pitch, sp += 4u * kVecPitch * 4u)
+                if (chunk_ok) cp_async_16(sp, gp);
+        }
+        cp_async_commit();
+    };
+    float acc = 0.f;
+    bool have = false;
+    load(0, 0);
+    int buf = 0;
+    for (int i0 = 0; i0 < dm.W; i0 += 32, buf ^= 1) {
+        load(i0 + 32, buf ^ 1);
+        cp_async_wait<1>();
+        __syncwarp();
+        float* tile = tile0 + (size_t)buf * kTileRows * kVecPitch;
+        const XTile g = geometry(i0);
+        // ---- sequential sums: lane = chain, step s handles column step j = s - grp ----
+        const int mb = fwd ? 0 : 31, ms = fwd ? 1 : -1;                   // memory column of column step j: mb + ms * j
+        const bool interior = g.ncols == 32 && g.r_lo == 0 && g.ybase + 64 <= dm.H;   // every chain element of the tile exists
+        if (interior && __all_sync(0xffffffffu, have)) {
+            float v[32 + kSkew];
+            int rr[32 + kSkew];
+#pragma unroll
+            for (int s = 0; s < 32 + kSkew; ++s) {
+                const int j = s - grp;
+                if (s >= kSkew && s < 32) {                                // all four groups are inside the tile
+                    rr[s] = (lane + __shfl_sync(0xffffffffu, g.off, j)) * kVecPitch + mb + ms * j;
+                    v[s] = tile[rr[s]];
+                } else {
+                    rr[s] = (lane + __shfl_sync(0xffffffffu, g.off, j & 31)) * kVecPitch + mb + ms * j;
+                    v[s] = (unsigned)j < 32u ? tile[rr[s]] : 0.f;
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < 32 + kSkew; ++s) {
+                if (s >= kSkew && s < 32) {
+                    acc = v[s] + acc;
+                    tile[rr[s]] = acc;
+                } else if ((unsigned)(s - grp) < 32u) {
+                    acc = v[s] + acc;
+                    tile[rr[s]] = acc;
+                }
+            }
+        } else {
+            float v[32 + kSkew];
+            int rr[32 + kSkew];
+#pragma unroll
+            for (int s = 0; s < 32 + kSkew; ++s) {
+                const int j = s - grp;
+                const int r = lane + __shfl_sync(0xffffffffu, g.off, j & 31);  // tile row of this lane's chain at column step j
+                const bool ok = (unsigned)j < (unsigned)g.ncols && r >= g.r_lo && r < g.r_hi;
+                rr[s] = ok ? r * kVecPitch + mb + ms * j : ((unsigned)j < (unsigned)g.ncols ? -1 : -2);
+                v[s] = ok ? tile[rr[s]] : 0.f;
+            }
+#pragma unroll
+            for (int s = 0; s < 32 + kSkew; ++s) {
+                if (rr[s] >= 0) {
+                    if (have) { acc = v[s] + acc; tile[rr[s]] = acc; }
+                    else { acc = v[s]; have = true; }
+                } else if (rr[s] == -1) {                                  // a column step of the image outside the plane
+                    have = false;
+                }
+            }
+        }
+        __syncwarp();
+        // ---- store: row r of the tile, lane = memory column; the element belongs to chain (r - off) ----
+        const int j_of_lane = fwd ? lane : 31 - lane;
+        const int off_m = __shfl_sync(0xffffffffu, g.off, j_of_lane);
+        const int xbase = fwd ? i0 : dm.W - 32 - i0;
+        float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (xbase + lane);
+        for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch)
+            if ((unsigned)(r - off_m) < 32u) *gp = tile[r * kVecPitch + lane];
         __syncwarp();
     }
 }
@@ -1106,13 +1239,20 @@ void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& i
     }
     if (any_y) integral_ymajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
     if (any_x) {
-        const size_t smem = (size_t)4 * 2 * kTileRows * kTilePitch * sizeof(float);
         static bool attr_set = false;
         if (!attr_set) {
-            cudaFuncSetAttribute(integral_xmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(integral_xmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(4 * 2 * kTileRows * kVecPitch * sizeof(float)));
+            cudaFuncSetAttribute(integral_xmajor_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(4 * 2 * kTileRows * kTilePitch * sizeof(float)));
             attr_set = true;
         }
-        integral_xmajor_kernel<<<grid, 128, smem, s>>>(d_planes, dm, ip, d_rtab, rlen);
+        static const bool force_scalar = [] { const char* e = getenv("FDCM_INTEGRAL_SCALAR"); return e && e[0] == '1'; }();
+        if (dm.W % 4 == 0 && !force_scalar)
+            integral_xmajor_kernel<<<grid, 128, (size_t)4 * 2 * kTileRows * kVecPitch * sizeof(float), s>>>(d_planes, dm, ip, d_rtab, rlen);
+        else
+            integral_xmajor_scalar_kernel<<<grid, 128, (size_t)4 * 2 * kTileRows * kTilePitch * sizeof(float), s>>>(d_planes, dm, ip, d_rtab,
+                                                                                                                 rlen);
     }
 }
 
