@@ -244,121 +244,174 @@ __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint
 }
 
 // =============================================================================================
-// fill (imgproc.h:122-128 incl. its in-place aliasing), one warp per row, lane = pixel of a 32-pixel chunk.
-// The row's envelope (vertex v, first owned pixel s, f(v) + v^2; s strictly increasing) is read 32 entries at a time,
-// one entry per lane.  The entries whose interval starts inside the chunk set one bit each in `marks`; the owner of
-// pixel p is the popc(marks & bits <= p)-th of them (or the entry carried over from the left).  The value a vertex
-// contributes is f(v) when it lies inside its own interval (s <= v) and the ALREADY WRITTEN out(v) when it lies left
-// of it (s > v): out(v) comes from the shared-memory copy of the row (earlier chunk) or from another lane of the same
-// chunk (resolved iteratively; the dependency always points to a lower entry index).
+// fill (imgproc.h:122-128 incl. its in-place aliasing): out(q) = base(owner(q)) + (q - v_owner)^2, lane = pixel of a
+// 32-pixel chunk.  The row's envelope (vertex v, first owned pixel s, f(v) + v^2; s strictly increasing) is read 32
+// entries at a time, one entry per lane.
+//   base: the reference's second loop writes out(q) = img(v) + (q-v)^2 while img(v) may already hold out(v).  A vertex
+//   inside its own interval (s <= v) contributes f(v); a vertex left of it (s > v) contributes out(v) = base(j) +
+//   (v - v_j)^2 with j the entry that owns pixel v (the last one with s_j <= v, normally one of the nearest few below).
+//   Bases are resolved once per batch, in registers: backward search by shuffles over the current and the previous
+//   batch, then propagation along the (downward pointing) dependencies; a global-memory walk covers the rest.
+//   fill: the entries whose interval starts inside the chunk set one bit each in `marks`; the owner of pixel p is the
+//   popc(marks & bits <= p)-th of them (or the entry carried over from the left).
 // =============================================================================================
-constexpr int kFillWarps = 4;
+struct RowFill {
+    const uint2* row;       // the row's entries
+    const uint2* sp;        // this lane's slot of the current 32-entry batch: row + e0 + lane
+    int K, e0, ci, nxt;     // entries; first entry of the batch; entries consumed; first pixel of entry ci (uniform)
+    uint2 be, nbe, pbe;     // batch entry of this lane (x = resolved base), same lane of the next (raw) / previous (resolved) batch
+    int carry_v;            // the entry that owns the pixel left of the current chunk (uniform)
+    uint32_t carry_b;
 
-__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
-    uint32_t v;
-    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
-    return v;
-}
-
-// [win_lo, win_lo + win_w): columns that can hold envelope vertices, both multiples of 32
-__global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint2* __restrict__ spill_all,
-                                                                      const int32_t* __restrict__ row_k,
-                                                                      float* __restrict__ planes, MapDims dm, int n_rows_total,
-                                                                      int maxdepth, int win_lo, int win_w) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int row = blockIdx.x * kFillWarps + warp;           // row of the [D*H][pitch] stack of planes
-    if (row >= n_rows_total) return;
-    // shared-memory copy of the row's window, addressed by absolute column: rb0 + 4 * q
-    const uint32_t rb0 = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)(warp * win_w - win_lo) * 4u;
-    const int W = dm.W;
-    float* op = planes + (size_t)row * dm.pitch + lane;       // this lane's pixel of the current chunk
-    const size_t prow = (size_t)(row / dm.H) * (size_t)(((dm.H + 31) >> 5) << 5) + (size_t)(row % dm.H);   // padded workspace row
-    const int K = row_k[prow];
-    if (K <= 0) {                                             // no edge pixel in this plane: FLT_MAX stays (imgproc.h:174)
-        for (int q = lane; q < W; q += 32, op += 32) *op = FLT_MAX;
-        return;
+    __device__ uint32_t slow_base(int idx) const {
+        uint32_t acc = 0;
+        int cur = idx;
+        while (true) {
+            const uint2 e = row[cur];
+            const int v = (int)(e.y & 0xFFFFu), s = (int)(e.y >> 16);
+            if (s <= v) return e.x - (uint32_t)(v * v) + acc;
+            int lo = 0, hi = cur - 1;            // largest o with s_o <= v (s_0 = 0)
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if ((int)(row[mid].y >> 16) <= v) lo = mid; else hi = mid - 1;
+            }
+            const int dd = v - (int)(row[lo].y & 0xFFFFu);
+            acc += (uint32_t)(dd * dd);
+            cur = lo;
+        }
     }
-    const uint2* sp = spill_all + prow * maxdepth + lane;
-    const uint2 kSentinel = make_uint2(0u, 0xFFFFFFFFu);      // s = 0xFFFF: never starts inside a chunk
-    uint2 be = lane < K ? sp[0] : kSentinel;
-    uint2 nbe = 32 + lane < K ? sp[32] : kSentinel;
-    int e0 = 0;                                               // the batch holds entries [e0, e0 + 32), one per lane
-    int bv = (int)(be.y & 0xFFFFu), bs = (int)(be.y >> 16);
-    uint32_t bf = be.x - (uint32_t)(bv * bv);
-    int carry_v = __shfl_sync(0xffffffffu, bv, 0);            // entry 0: s = 0 <= v
-    uint32_t carry_b = __shfl_sync(0xffffffffu, bf, 0);
-    int ci = 0;                                               // entries consumed so far (uniform)
-    int nxt = 0;                                              // first pixel of the first unconsumed entry (uniform)
-    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
-    const int win_hi = win_lo + win_w;
-    for (int q0 = 0; q0 < dm.pitch; q0 += 32, op += 32) {
-        const int q = q0 + lane;
+    __device__ __forceinline__ void resolve(int lane) {
+        const int bv = (int)(be.y & 0xFFFFu), bs = (int)(be.y >> 16);
+        uint32_t base = be.x - (uint32_t)(bv * bv);
+        const bool chain = e0 + lane < K && bs > bv;
+        if (__any_sync(0xffffffffu, chain)) {
+            // owner = the last entry with s <= v: s increases along the lanes, so five doubling steps find the last lane
+            // below this one that qualifies; the previous batch is searched the same way when there is none
+            int owner = -1;                      // lane of the owner entry; once found, negative = lane owner + 32 of the previous batch
+#pragma unroll
+            for (int step = 16; step >= 1; step >>= 1) {
+                const int t = owner + step;
+                const uint32_t y = __shfl_sync(0xffffffffu, be.y, t & 31);
+                if (t < lane && (int)(y >> 16) <= bv) owner = t;
+            }
+            bool found = !chain || owner >= 0;
+            if (__any_sync(0xffffffffu, !found)) {
+                int po = -1;
+#pragma unroll
+                for (int step = 32; step >= 1; step >>= 1) {            // lanes 0..31 (po + 32 = 31 first)
+                    const int t = po + step;
+                    const uint32_t y = __shfl_sync(0xffffffffu, pbe.y, t & 31);
+                    if (t <= 31 && (int)(y >> 16) <= bv) po = t;
+                }
+                if (!found && po >= 0) {
+                    owner = po - 32;
+                    found = true;
+                }
+            }
+            bool ready = !chain;
+            if (chain && !found) {               // owner further than 32 entries below: walk the global array
+                base = slow_base(e0 + lane);
+                ready = true;
+            }
+            const int src = owner & 31;
+            {
+                const uint32_t pb = __shfl_sync(0xffffffffu, pbe.x, src);
+                const int pv = (int)(__shfl_sync(0xffffffffu, pbe.y, src) & 0xFFFFu);
+                if (!ready && chain && owner < 0) {
+                    const int dd = bv - pv;
+                    base = pb + (uint32_t)(dd * dd);
+                    ready = true;
+                }
+            }
+            unsigned rdy = __ballot_sync(0xffffffffu, ready);
+            while (rdy != 0xFFFFFFFFu) {         // owners inside the batch: each round resolves at least the lowest pending lane
+                const uint32_t ob = __shfl_sync(0xffffffffu, base, src);
+                const int ov = __shfl_sync(0xffffffffu, bv, src);
+                if (!ready && ((rdy >> src) & 1u)) {
+                    const int dd = bv - ov;
+                    base = ob + (uint32_t)(dd * dd);
+                    ready = true;
+                }
+                rdy = __ballot_sync(0xffffffffu, ready);
+            }
+        }
+        be.x = base;
+    }
+    __device__ __forceinline__ void init(const uint2* row_entries, int k, int lane) {
+        const uint2 kSentinel = make_uint2(0u, 0xFFFFFFFFu);   // s = 0xFFFF: never starts inside a chunk
+        row = row_entries;
+        sp = row_entries + lane;
+        K = k; e0 = 0; ci = 0; nxt = k > 0 ? 0 : 0x7FFFFFFF;
+        be = lane < K ? sp[0] : kSentinel;
+        nbe = 32 + lane < K ? sp[32] : kSentinel;
+        pbe = kSentinel;
+        carry_v = 0; carry_b = 0;
+        resolve(lane);
+    }
+    // value of pixel q0 + lane; chunks must be visited left to right
+    __device__ __forceinline__ uint32_t chunk(int q0, int lane, uint32_t le_mask) {
         int ov = carry_v;
         uint32_t ob = carry_b;
         while (nxt < q0 + 32) {                               // some interval starts inside this chunk
             if (ci == e0 + 32) {                              // ... in the next 32 entries
                 e0 += 32;
+                sp += 32;
+                pbe = be;
                 be = nbe;
-                nbe = e0 + 32 + lane < K ? sp[e0 + 32] : kSentinel;
-                bv = (int)(be.y & 0xFFFFu);
-                bs = (int)(be.y >> 16);
-                bf = be.x - (uint32_t)(bv * bv);
+                nbe = e0 + 32 + lane < K ? sp[32] : make_uint2(0u, 0xFFFFFFFFu);
+                resolve(lane);
             }
-            const int rel = bs - q0;
+            const int bv = (int)(be.y & 0xFFFFu);
+            const int rel = (int)(be.y >> 16) - q0;
             const bool inb = (unsigned)rel < 32u;             // consecutive lanes starting at ci - e0 (s is increasing)
             const unsigned bal = __ballot_sync(0xffffffffu, inb);
             const unsigned marks = __reduce_or_sync(0xffffffffu, inb ? (1u << rel) : 0u);
-            const int first = ci - e0;
-            const bool chain = inb && bs > bv;
-            bool ready = !chain;
-            uint32_t base = bf;
-            const bool from_row = chain && bv < q0;
-            if (__any_sync(0xffffffffu, from_row)) {
-                __syncwarp();                                 // orders the earlier chunks' st.shared before this read
-                if (from_row) {
-                    base = lds_u32(rb0 + 4u * (uint32_t)bv);
-                    ready = true;
-                }
-            }
             const int c = __popc(marks & le_mask);
-            const int src = (first + c - 1) & 31;
-            unsigned pend = __ballot_sync(0xffffffffu, inb && !ready);
-            int pv;
-            uint32_t pb;
-            while (true) {
-                const uint32_t sb = __shfl_sync(0xffffffffu, base, src);
-                const int sv = __shfl_sync(0xffffffffu, bv, src);
-                pv = c ? sv : ov;
-                pb = c ? sb : ob;
-                if (!pend) break;
-                const int dq = q - pv;
-                const uint32_t val = pb + (uint32_t)(dq * dq);
-                const bool pok = c == 0 || !((pend >> src) & 1u);       // this pixel's owner already has its base
-                const int pix = (bv - q0) & 31;
-                const uint32_t vv = __shfl_sync(0xffffffffu, val, pix);
-                const unsigned okb = __ballot_sync(0xffffffffu, pok);
-                if (inb && !ready && ((okb >> pix) & 1u)) {
-                    base = vv;
-                    ready = true;
-                }
-                pend = __ballot_sync(0xffffffffu, inb && !ready);
-            }
-            ov = pv;
-            ob = pb;
+            const int src = (ci - e0 + c - 1) & 31;
+            const uint32_t sb = __shfl_sync(0xffffffffu, be.x, src);
+            const int sv = __shfl_sync(0xffffffffu, bv, src);
+            if (c) { ov = sv; ob = sb; }
             const int lastl = 31 - __clz(bal);
             carry_v = __shfl_sync(0xffffffffu, bv, lastl);
-            carry_b = __shfl_sync(0xffffffffu, base, lastl);
+            carry_b = __shfl_sync(0xffffffffu, be.x, lastl);
             ci += __popc(bal);
             if (ci >= K) nxt = 0x7FFFFFFF;
-            else if (ci < e0 + 32) nxt = __shfl_sync(0xffffffffu, bs, ci - e0);
+            else if (ci < e0 + 32) nxt = (int)(__shfl_sync(0xffffffffu, be.y, ci - e0) >> 16);
             else nxt = (int)(__shfl_sync(0xffffffffu, nbe.y, 0) >> 16);
         }
-        const int dq = q - ov;
-        const uint32_t val = ob + (uint32_t)(dq * dq);
-        if (q0 >= win_lo && q0 < win_hi) sts_u32(rb0 + 4u * (uint32_t)q, val);
-        if (q < W) *op = (float)val;                          // < 2^24: exact
+        const int dq = q0 + lane - ov;
+        return ob + (uint32_t)(dq * dq);
+    }
+};
+
+constexpr int kFillWarps = 4;
+
+__device__ __forceinline__ size_t padded_row(int row, int H) {   // [D*H] row id -> workspace row (32 rows per band)
+    return (size_t)(row / H) * (size_t)(((H + 31) >> 5) << 5) + (size_t)(row % H);
+}
+
+// stand-alone fill (stage-wise builds, depths without a fused kernel): one warp per row
+__global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint2* __restrict__ spill_all,
+                                                                      const int32_t* __restrict__ row_k,
+                                                                      float* __restrict__ planes, MapDims dm, int n_rows_total,
+                                                                      int maxdepth) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kFillWarps + warp;           // row of the [D*H][pitch] stack of planes
+    if (row >= n_rows_total) return;
+    const int W = dm.W;
+    float* op = planes + (size_t)row * dm.pitch + lane;       // this lane's pixel of the current chunk
+    const size_t prow = padded_row(row, dm.H);
+    const int K = row_k[prow];
+    if (K <= 0) {                                             // no edge pixel in this plane: FLT_MAX stays (imgproc.h:174)
+        for (int q = lane; q < W; q += 32, op += 32) *op = FLT_MAX;
+        return;
+    }
+    RowFill rf;
+    rf.init(spill_all + prow * maxdepth, K, lane);
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+    for (int q0 = 0; q0 < dm.pitch; q0 += 32, op += 32) {
+        const uint32_t val = rf.chunk(q0, lane, le_mask);
+        if (q0 + lane < W) *op = (float)val;                  // < 2^24: exact
     }
 }
 
@@ -405,16 +458,7 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int rows = dm.D * dm.H;
-    const int wl = ws.win_lo & ~31;
-    const int ww = ((ws.win_lo + ws.maxdepth + 31) & ~31) - wl;
-    const size_t smem = (size_t)kFillWarps * ww * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(dt_row_fill_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        attr_set = true;
-    }
-    dt_row_fill_kernel<<<cdiv_u(rows, kFillWarps), kFillWarps * 32, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, rows, ws.maxdepth,
-                                                                              wl, ww);
+    dt_row_fill_kernel<<<cdiv_u(rows, kFillWarps), kFillWarps * 32, 0, s>>>(ws.spill, ws.row_k, d_planes, dm, rows, ws.maxdepth);
 }
 
 }   // namespace fdcm
