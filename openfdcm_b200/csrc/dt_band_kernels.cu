@@ -415,6 +415,94 @@ __global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint
     }
 }
 
+// =============================================================================================
+// fused fill + propagateOrientation (matching/src/featuremaps/dt3cpu.cpp:77-107): one CTA per image row y.
+// Warp w fills the pixels [q0, q0 + kFPChunk) of its planes' row y into a shared-memory tile [D][kFPChunk]; then every
+// thread takes one pixel, runs the circular min-plus sweeps over its D values in registers (with the sqrt of the L2
+// transform, core/imgproc.h:191-192, applied on the way in) and writes the D results as coalesced row segments.  The
+// distance-transform planes are never written to or read back from HBM (2N bytes less than fill -> propagate).
+// =============================================================================================
+template <int D>
+struct FPConfig {
+    static constexpr int kPlanesPerWarp = 2;
+    static constexpr int kWarps = (D + kPlanesPerWarp - 1) / kPlanesPerWarp;
+    static constexpr int kThreads = kWarps * 32;
+    static constexpr int kChunk = kThreads;             // pixels per iteration = one per thread in the propagate phase
+};
+
+template <int D>
+__global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
+dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const int32_t* __restrict__ row_k, float* __restrict__ planes,
+                         MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first) {
+    using C = FPConfig<D>;
+    extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] squared distances (0xFFFFFFFF: FLT_MAX)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x;
+    const int Hp = ((dm.H + 31) >> 5) << 5;                  // workspace rows per plane
+    RowFill rf[C::kPlanesPerWarp];
+    int Kp[C::kPlanesPerWarp];
+#pragma unroll
+    for (int p = 0; p < C::kPlanesPerWarp; ++p) {
+        const int d = warp + p * C::kWarps;   // planes half a turn apart: envelope sizes peak near the horizontal planes
+        Kp[p] = 0;
+        if (d < D) {
+            const size_t prow = (size_t)d * Hp + y;
+            Kp[p] = row_k[prow];
+            rf[p].init(spill_all + prow * maxdepth, Kp[p], lane);
+        }
+    }
+    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+    for (int q0 = 0; q0 < dm.W; q0 += C::kChunk) {
+        // ---- fill ----
+#pragma unroll
+        for (int p = 0; p < C::kPlanesPerWarp; ++p) {
+            const int d = warp + p * C::kWarps;
+            if (d < D) {
+                uint32_t* trow = fp_tile + (size_t)d * C::kChunk + lane;
+                if (Kp[p] > 0) {
+                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = rf[p].chunk(q0 + c, lane, le_mask);
+                } else {
+                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = 0xFFFFFFFFu;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- propagate: one pixel per thread ----
+        const int x = q0 + (int)threadIdx.x;
+        if (x < dm.W) {
+            float v[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const uint32_t u = fp_tile[(size_t)d * C::kChunk + threadIdx.x];
+                v[d] = u == 0xFFFFFFFFu ? FLT_MAX : (float)u;
+            }
+            if (sqrt_first) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) v[d] = sqrtf(v[d]);
+            }
+            constexpr int fwd = (3 * D + 1) / 2;
+            constexpr int bwd = D + (3 * D) / 2;
+#pragma unroll
+            for (int c = 0; c < fwd; ++c) {
+                const int c1 = (D + ((c - 1) % D)) % D;
+                const int c2 = c % D;
+                v[c2] = fminf(v[c2], v[c1] + pp.w[c]);
+            }
+#pragma unroll
+            for (int j = 0; j < bwd; ++j) {
+                const int c = D - j;
+                const int c1 = (D + ((c + 1) % D)) % D;
+                const int c2 = (D + (c % D)) % D;
+                v[c2] = fminf(v[c2], v[c1] + pp.w[fwd + j]);
+            }
+            float* op = planes + (size_t)y * dm.pitch + x;
+#pragma unroll
+            for (int d = 0; d < D; ++d) op[(size_t)d * dm.plane_elems] = v[d];
+        }
+        __syncthreads();
+    }
+}
+
 static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 
 int dt_band_count(const MapDims& dm) { return (dm.H + 31) / 32; }
@@ -459,6 +547,21 @@ void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int rows = dm.D * dm.H;
     dt_row_fill_kernel<<<cdiv_u(rows, kFillWarps), kFillWarps * 32, 0, s>>>(ws.spill, ws.row_k, d_planes, dm, rows, ws.maxdepth);
+}
+
+bool dt_fill_propagate_supported(const MapDims& dm) { return dm.D == 30; }
+
+void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,
+                              bool sqrt_first, cudaStream_t s) {
+    const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
+    using C = FPConfig<30>;
+    const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(dt_fill_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set = true;
+    }
+    dt_fill_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, ws.maxdepth, pp, sqrt_first ? 1 : 0);
 }
 
 }   // namespace fdcm

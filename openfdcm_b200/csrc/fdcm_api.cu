@@ -203,6 +203,7 @@ struct fdcm_dt3 {
     PropParams prop{};
     IntegralParams integ{};
     DevBuf planes, mask, g, stack, lines, bins, rtab, band_info, band_spill;
+    bool fuse_fill = true;      // FDCM_FUSE_FILL=0: separate fill and propagate kernels (A/B testing)
     int row_mode = 0;           // exact-regime row pass: 0 = band kernel (default), 1 = literal, 2 = warp-per-row interval refinement
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
@@ -329,6 +330,8 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
         m->row_literal = e && e[0] == '1';
         const char* e2 = std::getenv("FDCM_ROW_MODE");   // A/B testing of the exact-regime row kernels
         m->row_mode = m->row_literal ? 1 : (e2 ? std::atoi(e2) : 0);
+        const char* e3 = std::getenv("FDCM_FUSE_FILL");
+        m->fuse_fill = !(e3 && e3[0] == '0');
     }
 
     // translated scene (core/math.h:352-354) and orientation bins with the host libm (dt3cpu.h:123-134)
@@ -411,6 +414,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
         launch_raster(m->lines.as<float>(), m->bins.as<int32_t>(), m->n_lines, dm, m->mask.as<uint32_t>(), s);
     }
     const int dist = m->params.distance;
+    bool fused_propagate = false;
     if (m->exact && dist != FDCM_L1 && m->row_mode == 0) {
         {
             KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
@@ -420,8 +424,14 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
             launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, s);
         }
-        KernelScope k("dt_row_fill", N, s);
-        launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+        fused_propagate = m->stage != 1 && m->fuse_fill && dt_fill_propagate_supported(dm);
+        if (fused_propagate) {
+            KernelScope k("dt_fill_propagate", N, s);
+            launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, s);
+        } else {
+            KernelScope k("dt_row_fill", N, s);
+            launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+        }
     } else if (m->exact) {
         {
             KernelScope k("dt_col_exact", N / 2, s);
@@ -467,7 +477,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             launch_sqrt(m->planes.as<float>(), dm, s);
         }
     } else {
-        {
+        if (!fused_propagate) {
             KernelScope k("propagate", 2 * N, s);
             launch_propagate(m->planes.as<float>(), dm, m->prop, need_sqrt, s);
         }

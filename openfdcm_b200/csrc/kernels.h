@@ -25,6 +25,10 @@ void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info,
 // d_info (band records) or d_g (explicit u16 rows, tests) feeds the envelope build; exactly one of them is non-null
 void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
+// fill fused with propagateOrientation (and the L2 sqrt): the distance-transform planes never reach HBM
+bool dt_fill_propagate_supported(const MapDims& dm);
+void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,
+                              bool sqrt_first, cudaStream_t s);
 
 // ---- search_kernels.cu ----
 struct MapView {                 // read-only view of a built feature map
