@@ -559,6 +559,167 @@ __global__ void __launch_bounds__(128) search8_kernel(const __grid_constant__ Ma
     }
 }
 
+// =============================================================================================
+// K5+K6, warp-per-hypothesis version: lanes = consecutive candidate translations.
+// BatchOptimize scores the translations j * (svx, svy), j integer, and (svx, svy) has one unit component
+// (rasterizeVector), so the candidates of a hypothesis lie on a discrete line and the lookups of all candidates for
+// one template-line end point form a STREAK of adjacent pixels.  Lane l scores multiplier lo + l: one gather
+// instruction then touches a handful of 128-byte lines instead of 32 unrelated ones (the L1TEX wavefront count is
+// what bounds this kernel), and every lane runs Eigen's packet-4 / 2x-unrolled summation order on its own, so no
+// cross-lane reduction is needed.  Scores are pure functions of the multiplier: a window of up to 32 multipliers
+// around 0 is scored up front (it contains the first batch of either direction, which the reference always
+// evaluates), further ranges on demand; the control flow of batchoptimize.cpp:51-94 then consumes them in order.
+// =============================================================================================
+__global__ void __launch_bounds__(128) search_warp_kernel(const __grid_constant__ MapView map,
+                                                          const __grid_constant__ SlopeTableDev table,
+                                                          const __grid_constant__ TemplatesView tv,
+                                                          const __grid_constant__ SceneView sv,
+                                                          const __grid_constant__ SearchLaunch sl,
+                                                          const __grid_constant__ SearchOutputs out) {
+    extern __shared__ uint8_t s_bins[];   // [warp of the block][line]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long slot_idx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+    if (slot_idx >= sl.n_hyp) return;     // whole warp
+    const long long h = sl.perm ? (long long)sl.perm[slot_idx] : slot_idx;
+    uint8_t* bins = s_bins + (size_t)warp * tv.max_lines;
+    unsigned long long n_eval = 0;
+    bool valid = false;
+
+    int t, l0, L;
+    float avx, avy;
+    Rigid T;
+    if (sl.direct_align) {
+        // optimize<BatchOptimize>(templates, alignments, featuremap) (batchoptimize.cpp:6-123): template h as given
+        t = (int)h;
+        l0 = tv.offsets[t];
+        L = tv.offsets[t + 1] - l0;
+        T = Rigid{1.f, 0.f, 0.f, 0.f, 1.f, 0.f};      // x*1 + y*0 + 0 is exact: coordinates pass through unchanged
+        avx = sl.direct_align[h].x;
+        avy = sl.direct_align[h].y;
+    } else {
+        const HypDecode d = decode_hypothesis(h, tv, sv, sl);
+        t = d.t; l0 = d.l0; L = d.L;
+        if (lane == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);
+        T = align_dev(tv.lines[l0 + d.tline], sv.lines[d.sline], d.rev, avx, avy);   // defaultmatch.cpp:57-69
+    }
+    const float4* TL = tv.lines + l0;
+    const float asum = fabsf(avx) + fabsf(avy);
+    const bool null_vec = (double)asum <= (double)FLT_EPSILON + 1e-10 * (double)asum;   // batchoptimize.cpp:20
+    if (!null_vec) {
+        float svx, svy;
+        rasterize_vector_dev(avx, avy, svx, svy);
+        // bbox of the aligned template + orientation plane of every line (lane takes lines lane, lane+32, ...)
+        float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+        for (int i = lane; i < L; i += 32) {
+            const float4 p = __ldg(TL + i);
+            float ax, ay, bx, by;
+            xform(T, p.x, p.y, ax, ay);
+            xform(T, p.z, p.w, bx, by);
+            mnx = fminf(mnx, fminf(ax, bx)); mxx = fmaxf(mxx, fmaxf(ax, bx));
+            mny = fminf(mny, fminf(ay, by)); mxy = fmaxf(mxy, fmaxf(ay, by));
+            bins[i] = (uint8_t)bin_of_slope_dev(table, (by - ay) / (bx - ax));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+            mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+        }
+        __syncwarp();
+        float min_mul, max_mul;
+        minmax_dev(mnx + map.shift_x, mny + map.shift_y, mxx + map.shift_x, mxy + map.shift_y, (float)map.dm.W,
+                   (float)map.dm.H, svx, svy, min_mul, max_mul);
+        if (isfinite(min_mul) && isfinite(max_mul)) {
+            const float* planes = map.planes;
+            const unsigned pitch = (unsigned)map.dm.pitch;
+            const int Wm1 = map.dm.W - 1, Hm1 = map.dm.H - 1;
+            const long long maxm = trunc_ll(max_mul), minm = trunc_ll(min_mul);
+            // score of multiplier m on this lane (dt3cpu.cpp:126-179)
+            auto score_of = [&](long long mult) -> float {
+                const float m = (float)mult;
+                const float offx = map.shift_x + m * svx, offy = map.shift_y + m * svy;   // sceneTranslation + translation
+                return eigen_sum_lazy(L, [&](int i) {
+                    const float4 p = __ldg(TL + i);
+                    float ax, ay, bx, by;
+                    xform(T, p.x, p.y, ax, ay);
+                    xform(T, p.z, p.w, bx, by);
+                    int x1 = (int)(ax + offx), y1 = (int)(ay + offy), x2 = (int)(bx + offx), y2 = (int)(by + offy);
+                    x1 = min(max(x1, 0), Wm1); x2 = min(max(x2, 0), Wm1);   // guards only (no-ops inside the
+                    y1 = min(max(y1, 0), Hm1); y2 = min(max(y2, 0), Hm1);   // minmaxTranslation bounds)
+                    const float* P = planes + (size_t)bins[i] * map.dm.plane_elems;
+                    return fabsf(__ldg(P + ((unsigned)y1 * pitch + (unsigned)x1)) - __ldg(P + ((unsigned)y2 * pitch + (unsigned)x2)));
+                });
+            };
+            // cached range of scores: lane l holds the score of multiplier c_lo + l, l < c_n
+            long long c_lo = 0;
+            int c_n = 0;
+            float c_score = 0.f;
+            auto fill_cache = [&](long long lo, long long hi) {   // lo <= hi, hi - lo < 32, both inside [minm, maxm]
+                c_lo = lo;
+                c_n = (int)(hi - lo + 1);
+                if (lane < c_n) c_score = score_of(lo + lane);
+                __syncwarp();
+            };
+            // score of multiplier j (uniform); dir = direction in which further multipliers will be asked for
+            auto score_at = [&](long long j, int dir) -> float {
+                if (j < c_lo || j >= c_lo + c_n) {
+                    if (dir > 0) fill_cache(j, min(maxm, j + 31));
+                    else fill_cache(max(minm, j - 31), j);
+                }
+                return __shfl_sync(0xffffffffu, c_score, (int)(j - c_lo));
+            };
+            const long long B = sl.batch;
+            {   // first window: 0, the first batch of both directions when it fits, as much around 0 as 32 lanes hold
+                long long lo = max(minm, -15LL), hi = min(maxm, 16LL);
+                if (B > 15) { lo = max(minm, 0LL); hi = min(maxm, 31LL); }
+                if (lo > 0) lo = 0;            // (limits always include 0: the template is inside the map at t = 0)
+                if (hi < 0) hi = 0;
+                fill_cache(lo, hi);
+            }
+            float back = score_at(0, 1);                  // scores.back()
+            n_eval += 1;
+            float best = back, best_tx = 0.f, best_ty = 0.f;
+            for (int dir = 1; dir >= -1; dir -= 2) {
+                // batchoptimize.cpp:51-71 (dir = +1) and :74-94 (dir = -1)
+                const long long lim = dir > 0 ? maxm : -minm;     // multipliers run 1..lim in units of dir
+                for (long long kk = 1; kk <= lim; kk += B) {
+                    const long long jend = min(kk + B - 1, lim);
+                    float bmin = 0.f, blast = 0.f;
+                    long long barg = kk;
+                    for (long long j = kk; j <= jend; ++j) {
+                        const float sj = score_at(dir * j, dir);
+                        if (j == kk || sj < bmin) { bmin = sj; barg = j; }   // std::min_element: first minimum
+                        blast = sj;
+                    }
+                    n_eval += (unsigned long long)(jend - kk + 1);
+                    if (bmin > back) break;
+                    back = bmin;
+                    if (bmin < best) {
+                        best = bmin;
+                        best_tx = (float)(dir * barg) * svx;
+                        best_ty = (float)(dir * barg) * svy;
+                    }
+                    if (bmin < blast) break;
+                }
+            }
+            valid = true;
+            if (lane == 0) {
+                fdcm_match m;   // Match{tmplIdx, score, combine(translation, T)} (defaultmatch.cpp:82-84)
+                m.tmpl_idx = t + sl.tmpl_idx_base;
+                m.score = tv.denom ? best / tv.denom[t] : best;
+                m.transform[0] = T.r00; m.transform[1] = T.r01; m.transform[2] = T.tx + best_tx;
+                m.transform[3] = T.r10; m.transform[4] = T.r11; m.transform[5] = T.ty + best_ty;
+                out.rec[h] = m;
+            }
+        }
+    }
+    if (lane == 0) {
+        out.valid[h] = valid ? 1 : 0;
+        atomicAdd(out.counters + 0, n_eval);
+        atomicAdd(out.counters + 1, n_eval * 2ull * (unsigned long long)L);
+        atomicAdd(out.counters + 2, valid ? 1ull : 0ull);
+    }
+}
+
 void launch_search(const MapView& map, const SlopeTableDev& table, const TemplatesView& tv, const SceneView& sv,
                    const SearchLaunch& sl, const SearchOutputs& out, cudaStream_t s) {
     if (sl.n_hyp <= 0) return;
@@ -572,11 +733,20 @@ void launch_search(const MapView& map, const SlopeTableDev& table, const Templat
         search_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
         return;
     }
-    const int threads = 128, hyps = threads / kGroup;
+    static const bool use_v2 = [] { const char* e = getenv("FDCM_SEARCH_V2"); return e && e[0] == '1'; }();
+    if (use_v2) {                       // 8 lanes per hypothesis (kept for A/B measurements)
+        const int threads = 128, hyps = threads / kGroup;
+        const size_t smem = (size_t)hyps * tv.max_lines;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(search8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const unsigned grid = (unsigned)((sl.n_hyp + hyps - 1) / hyps);
+        search8_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
+        return;
+    }
+    const int threads = 128, hyps = threads / 32;
     const size_t smem = (size_t)hyps * tv.max_lines;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(search8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)((sl.n_hyp + hyps - 1) / hyps);
-    search8_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
+    search_warp_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
 }
 
 // =============================================================================================
