@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(128) search8_kernel(const __grid_constant__ Ma
 // around 0 is scored up front (it contains the first batch of either direction, which the reference always
 // evaluates), further ranges on demand; the control flow of batchoptimize.cpp:51-94 then consumes them in order.
 // =============================================================================================
-__global__ void __launch_bounds__(128) search_warp_kernel(const __grid_constant__ MapView map,
+__global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_constant__ MapView map,
                                                           const __grid_constant__ SlopeTableDev table,
                                                           const __grid_constant__ TemplatesView tv,
                                                           const __grid_constant__ SceneView sv,
@@ -632,9 +632,10 @@ __global__ void __launch_bounds__(128) search_warp_kernel(const __grid_constant_
             const float* planes = map.planes;
             const unsigned pitch = (unsigned)map.dm.pitch;
             const int Wm1 = map.dm.W - 1, Hm1 = map.dm.H - 1;
-            const long long maxm = trunc_ll(max_mul), minm = trunc_ll(min_mul);
+            // (long) conversions of batchoptimize.cpp:51,74; |multiplier| < map side <= 65534, so int arithmetic is exact
+            const int maxm = (int)min(max(trunc_ll(max_mul), -70000LL), 70000LL), minm = (int)min(max(trunc_ll(min_mul), -70000LL), 70000LL);
             // score of multiplier m on this lane (dt3cpu.cpp:126-179)
-            auto score_of = [&](long long mult) -> float {
+            auto score_of = [&](int mult) -> float {
                 const float m = (float)mult;
                 const float offx = map.shift_x + m * svx, offy = map.shift_y + m * svy;   // sceneTranslation + translation
                 return eigen_sum_lazy(L, [&](int i) {
@@ -650,27 +651,31 @@ __global__ void __launch_bounds__(128) search_warp_kernel(const __grid_constant_
                 });
             };
             // cached range of scores: lane l holds the score of multiplier c_lo + l, l < c_n
-            long long c_lo = 0;
-            int c_n = 0;
+            int c_lo = 0, c_n = 0;
             float c_score = 0.f;
-            auto fill_cache = [&](long long lo, long long hi) {   // lo <= hi, hi - lo < 32, both inside [minm, maxm]
+            auto fill_cache = [&](int lo, int hi) {   // lo <= hi, hi - lo < 32, both inside [minm, maxm]
                 c_lo = lo;
-                c_n = (int)(hi - lo + 1);
+                c_n = hi - lo + 1;
                 if (lane < c_n) c_score = score_of(lo + lane);
                 __syncwarp();
             };
             // score of multiplier j (uniform); dir = direction in which further multipliers will be asked for
-            auto score_at = [&](long long j, int dir) -> float {
+            // Ranges are as wide as one batch (every candidate of a started batch is evaluated by the reference) or, for
+            // small batches, as wide as the warp: a few speculative scores cost less than idle lanes.
+            const int B = sl.batch;
+            const int span = B >= 8 ? min(B, 32) : 32;
+            auto score_at = [&](int j, int dir) -> float {
                 if (j < c_lo || j >= c_lo + c_n) {
-                    if (dir > 0) fill_cache(j, min(maxm, j + 31));
-                    else fill_cache(max(minm, j - 31), j);
+                    if (dir > 0) fill_cache(j, min(maxm, j + span - 1));
+                    else fill_cache(max(minm, j - span + 1), j);
                 }
-                return __shfl_sync(0xffffffffu, c_score, (int)(j - c_lo));
+                return __shfl_sync(0xffffffffu, c_score, j - c_lo);
             };
-            const long long B = sl.batch;
-            {   // first window: 0, the first batch of both directions when it fits, as much around 0 as 32 lanes hold
-                long long lo = max(minm, -15LL), hi = min(maxm, 16LL);
-                if (B > 15) { lo = max(minm, 0LL); hi = min(maxm, 31LL); }
+            {   // first window: 0 and the first batch of both directions when they fit into the warp
+                int lo, hi;
+                if (2 * span + 1 <= 32) { lo = max(minm, -span); hi = min(maxm, span); }
+                else if (span >= 16) { lo = 0; hi = min(maxm, span - 1); }           // 0 and most of the first batch upwards
+                else { lo = max(minm, -15); hi = min(maxm, 16); }
                 if (lo > 0) lo = 0;            // (limits always include 0: the template is inside the map at t = 0)
                 if (hi < 0) hi = 0;
                 fill_cache(lo, hi);
@@ -680,12 +685,12 @@ __global__ void __launch_bounds__(128) search_warp_kernel(const __grid_constant_
             float best = back, best_tx = 0.f, best_ty = 0.f;
             for (int dir = 1; dir >= -1; dir -= 2) {
                 // batchoptimize.cpp:51-71 (dir = +1) and :74-94 (dir = -1)
-                const long long lim = dir > 0 ? maxm : -minm;     // multipliers run 1..lim in units of dir
-                for (long long kk = 1; kk <= lim; kk += B) {
-                    const long long jend = min(kk + B - 1, lim);
+                const int lim = dir > 0 ? maxm : -minm;           // multipliers run 1..lim in units of dir
+                for (int kk = 1; kk <= lim; kk += B) {
+                    const int jend = min(kk + B - 1, lim);
                     float bmin = 0.f, blast = 0.f;
-                    long long barg = kk;
-                    for (long long j = kk; j <= jend; ++j) {
+                    int barg = kk;
+                    for (int j = kk; j <= jend; ++j) {
                         const float sj = score_at(dir * j, dir);
                         if (j == kk || sj < bmin) { bmin = sj; barg = j; }   // std::min_element: first minimum
                         blast = sj;
