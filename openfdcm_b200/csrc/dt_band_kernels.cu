@@ -430,6 +430,44 @@ struct FPConfig {
     static constexpr int kChunk = kThreads;             // pixels per iteration = one per thread in the propagate phase
 };
 
+// propagate phase shared by the fused kernels: thread t takes pixel q0 + t of image row y, reads its D values from the
+// tile (0xFFFFFFFF: FLT_MAX), runs the forward (ceil(1.5 D)) and backward (D + floor(1.5 D)) circular sweeps
+// P[c2] = min(P[c2], P[c1] + w_step) in registers and writes D coalesced row segments.
+template <int D>
+__device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int chunk, int q0, int y, float* __restrict__ planes,
+                                                    const MapDims& dm, const PropParams& pp, int sqrt_first) {
+    const int x = q0 + (int)threadIdx.x;
+    if (x >= dm.W) return;
+    float v[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const uint32_t u = tile[(size_t)d * chunk + threadIdx.x];
+        v[d] = u == 0xFFFFFFFFu ? FLT_MAX : (float)u;
+    }
+    if (sqrt_first) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[d] = sqrtf(v[d]);
+    }
+    constexpr int fwd = (3 * D + 1) / 2;
+    constexpr int bwd = D + (3 * D) / 2;
+#pragma unroll
+    for (int c = 0; c < fwd; ++c) {
+        const int c1 = (D + ((c - 1) % D)) % D;
+        const int c2 = c % D;
+        v[c2] = fminf(v[c2], v[c1] + pp.w[c]);
+    }
+#pragma unroll
+    for (int j = 0; j < bwd; ++j) {
+        const int c = D - j;
+        const int c1 = (D + ((c + 1) % D)) % D;
+        const int c2 = (D + (c % D)) % D;
+        v[c2] = fminf(v[c2], v[c1] + pp.w[fwd + j]);
+    }
+    float* op = planes + (size_t)y * dm.pitch + x;
+#pragma unroll
+    for (int d = 0; d < D; ++d) op[(size_t)d * dm.plane_elems] = v[d];
+}
+
 template <int D>
 __global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
 dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const int32_t* __restrict__ row_k, float* __restrict__ planes,
@@ -468,37 +506,129 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const int32_t* __r
         }
         __syncthreads();
         // ---- propagate: one pixel per thread ----
-        const int x = q0 + (int)threadIdx.x;
-        if (x < dm.W) {
-            float v[D];
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const uint32_t u = fp_tile[(size_t)d * C::kChunk + threadIdx.x];
-                v[d] = u == 0xFFFFFFFFu ? FLT_MAX : (float)u;
-            }
-            if (sqrt_first) {
-#pragma unroll
-                for (int d = 0; d < D; ++d) v[d] = sqrtf(v[d]);
-            }
-            constexpr int fwd = (3 * D + 1) / 2;
-            constexpr int bwd = D + (3 * D) / 2;
-#pragma unroll
-            for (int c = 0; c < fwd; ++c) {
-                const int c1 = (D + ((c - 1) % D)) % D;
-                const int c2 = c % D;
-                v[c2] = fminf(v[c2], v[c1] + pp.w[c]);
-            }
-#pragma unroll
-            for (int j = 0; j < bwd; ++j) {
-                const int c = D - j;
-                const int c1 = (D + ((c + 1) % D)) % D;
-                const int c2 = (D + (c % D)) % D;
-                v[c2] = fminf(v[c2], v[c1] + pp.w[fwd + j]);
-            }
-            float* op = planes + (size_t)y * dm.pitch + x;
-#pragma unroll
-            for (int d = 0; d < D; ++d) op[(size_t)d * dm.plane_elems] = v[d];
+        propagate_from_tile<D>(fp_tile, C::kChunk, q0, y, planes, dm, pp, sqrt_first);
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
+// L1 transform (core/imgproc.h:137-146,178-184): the second (row) call is two min-plus sweeps, on integers
+// out(x) = min(x + min_{v<=x}(g(v) - v), -x + min_{v>=x}(g(v) + v)), g = vertical distance from the band records.
+// Lane = column.  A first right-to-left pass leaves the suffix minimum of g(v) + v per 32-column chunk in shared
+// memory; the fill then walks left to right with a warp prefix-min scan (carry across chunks) and a suffix-min
+// scan inside the chunk.  Exact at any map size; no envelope, no workspace.
+// =============================================================================================
+constexpr int kBigL1 = 1 << 28;
+
+struct L1Fill {
+    const uint2* info;      // band records of (plane, band of the row), this lane's column of chunk 0: + lane
+    int* S;                 // shared: S[c] = min over columns >= 32c of g(v) + v, S[nchunks] = big
+    int r, W, pitch, carry;
+    uint32_t mle, mge;
+    uint2 e_next;           // record of this lane's column in the next chunk to be visited (loaded one step ahead)
+
+    __device__ __forceinline__ uint2 load(int x) const {
+        return (x >= 0 && x < W) ? info[x - (int)(threadIdx.x & 31)] : make_uint2(0u, 0xFFFFFFFFu);
+    }
+    __device__ __forceinline__ int g_of(const uint2 e) const {   // vertical distance of this row in the record's column, or big
+        if (e.x == 0u && e.y == 0xFFFFFFFFu) return kBigL1;
+        const uint32_t above = e.x & mle, below = e.x & mge;
+        const int upd = r + (above ? __clz(above) - 31 : (int)(e.y & 0xFFFFu));
+        const int dnd = (31 - r) + (below ? __ffs(below) - 1 - 31 : (int)(e.y >> 16));
+        return min(upd, dnd);
+    }
+    __device__ __forceinline__ void init(const uint2* info_row, int row_in_band, int width, int pitch_, int* s_suffix, int lane) {
+        info = info_row + lane;
+        S = s_suffix;
+        r = row_in_band;
+        W = width;
+        pitch = pitch_;
+        carry = kBigL1;
+        mle = 0xFFFFFFFFu >> (31 - r);
+        mge = 0xFFFFFFFFu << r;
+        const int nch = pitch >> 5;
+        int run = kBigL1;
+        if (lane == 0) S[nch] = kBigL1;
+        uint2 e = load((nch - 1) * 32 + lane);
+        for (int c = nch - 1; c >= 0; --c) {
+            const uint2 ec = e;
+            e = load((c - 1) * 32 + lane);
+            const int x = c * 32 + lane;
+            const int g = g_of(ec);
+            run = min(run, __reduce_min_sync(0xffffffffu, g >= kBigL1 ? kBigL1 : g + x));
+            if (lane == 0) S[c] = run;
         }
+        e_next = load(lane);
+        __syncwarp();
+    }
+    // value of pixel q0 + lane (0xFFFFFFFF: FLT_MAX); chunks must be visited left to right
+    __device__ __forceinline__ uint32_t chunk(int q0, int lane) {
+        const int x = q0 + lane;
+        const uint2 e = e_next;
+        e_next = load(x + 32);
+        const int g = g_of(e);
+        int a = g >= kBigL1 ? kBigL1 : g - x;
+        int b = g >= kBigL1 ? kBigL1 : g + x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_down_sync(0xffffffffu, b, o);
+            if (lane >= o) a = min(a, ta);
+            if (lane + o < 32) b = min(b, tb);
+        }
+        a = min(a, carry);
+        carry = __shfl_sync(0xffffffffu, a, 31);
+        b = min(b, S[(q0 >> 5) + 1]);
+        const int v = min(a + x, b - x);
+        return v >= (kBigL1 >> 1) ? 0xFFFFFFFFu : (uint32_t)v;
+    }
+};
+
+// stand-alone L1 row call: one warp per row
+__global__ void __launch_bounds__(kFillWarps * 32) dt_row_l1_band_kernel(const uint2* __restrict__ info, float* __restrict__ planes,
+                                                                         MapDims dm, int nbands, int n_rows_total) {
+    extern __shared__ __align__(16) int l1_suffix[];          // [kFillWarps][nchunks + 1]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kFillWarps + warp;
+    if (row >= n_rows_total) return;
+    const int d = row / dm.H, y = row % dm.H;
+    const int nch = dm.pitch >> 5;
+    L1Fill lf;
+    lf.init(info + ((size_t)d * nbands + (y >> 5)) * dm.pitch, y & 31, dm.W, dm.pitch, l1_suffix + warp * (nch + 1), lane);
+    float* op = planes + (size_t)row * dm.pitch + lane;
+    for (int q0 = 0; q0 < dm.pitch; q0 += 32, op += 32) {
+        const uint32_t v = lf.chunk(q0, lane);
+        if (q0 + lane < dm.W) *op = v == 0xFFFFFFFFu ? FLT_MAX : (float)v;
+    }
+}
+
+// fused L1 row call + propagateOrientation: same structure as dt_fill_propagate_kernel
+template <int D>
+__global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
+dt_l1_propagate_kernel(const uint2* __restrict__ info, float* __restrict__ planes, MapDims dm, int nbands,
+                       const __grid_constant__ PropParams pp) {
+    using C = FPConfig<D>;
+    extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] distances, then [D][nchunks + 1] suffix minima
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int y = blockIdx.x;
+    const int nch = dm.pitch >> 5;
+    int* suffix = reinterpret_cast<int*>(fp_tile + (size_t)D * C::kChunk);
+    L1Fill lf[C::kPlanesPerWarp];
+#pragma unroll
+    for (int p = 0; p < C::kPlanesPerWarp; ++p) {
+        const int d = warp + p * C::kWarps;
+        if (d < D) lf[p].init(info + ((size_t)d * nbands + (y >> 5)) * dm.pitch, y & 31, dm.W, dm.pitch, suffix + d * (nch + 1), lane);
+    }
+    for (int q0 = 0; q0 < dm.W; q0 += C::kChunk) {
+#pragma unroll
+        for (int p = 0; p < C::kPlanesPerWarp; ++p) {
+            const int d = warp + p * C::kWarps;
+            if (d < D) {
+                uint32_t* trow = fp_tile + (size_t)d * C::kChunk + lane;
+                for (int c = 0; c < C::kChunk; c += 32) trow[c] = (q0 + c < dm.pitch) ? lf[p].chunk(q0 + c, lane) : 0xFFFFFFFFu;
+            }
+        }
+        __syncthreads();
+        propagate_from_tile<D>(fp_tile, C::kChunk, q0, y, planes, dm, pp, 0);
         __syncthreads();
     }
 }
@@ -518,6 +648,11 @@ void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info,
     const int nbands = dt_band_count(dm);
     const size_t smem = (size_t)nbands * 64 * 6;
     dim3 grid((dm.wwords + 1) / 2, dm.D);
+    static size_t attr_smem = 48 * 1024;
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(dt_col_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_smem = smem;
+    }
     dt_col_band_kernel<<<grid, 256, smem, s>>>(d_mask, dm, reinterpret_cast<uint2*>(d_info), nbands);
 }
 
@@ -562,6 +697,32 @@ void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, in
         attr_set = true;
     }
     dt_fill_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, ws.maxdepth, pp, sqrt_first ? 1 : 0);
+}
+
+void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& dm, cudaStream_t s) {
+    const int nbands = dt_band_count(dm), rows = dm.D * dm.H;
+    const size_t smem = (size_t)kFillWarps * ((dm.pitch >> 5) + 1) * sizeof(int);
+    dt_row_l1_band_kernel<<<cdiv_u(rows, kFillWarps), kFillWarps * 32, smem, s>>>(reinterpret_cast<const uint2*>(d_info), d_planes, dm,
+                                                                                 nbands, rows);
+}
+
+void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& dm, const PropParams& pp, cudaStream_t s) {
+    using C = FPConfig<30>;
+    const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch >> 5) + 1) * sizeof(int);
+    static size_t attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaFuncSetAttribute(dt_l1_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_smem = smem;
+    }
+    dt_l1_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(reinterpret_cast<const uint2*>(d_info), d_planes, dm, dt_band_count(dm), pp);
+}
+
+// shared memory the band kernels need for this map (column transposition, fused L1 tile); callers fall back to the
+// first-generation kernels when it exceeds what one CTA can have
+size_t dt_band_smem_bytes(const MapDims& dm) {
+    const size_t col = (size_t)dt_band_count(dm) * 64 * 6;
+    const size_t l1 = (size_t)30 * FPConfig<30>::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch >> 5) + 1) * sizeof(int);
+    return col > l1 ? col : l1;
 }
 
 }   // namespace fdcm

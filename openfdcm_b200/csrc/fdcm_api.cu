@@ -203,6 +203,7 @@ struct fdcm_dt3 {
     PropParams prop{};
     IntegralParams integ{};
     DevBuf planes, mask, g, stack, lines, bins, rtab, band_info, band_spill;
+    bool band_path = false, band_l1 = false;   // which distance-transform formulation this map uses (set by prepare)
     bool fuse_fill = true;      // FDCM_FUSE_FILL=0: separate fill and propagate kernels (A/B testing)
     int row_mode = 0;           // exact-regime row pass: 0 = band kernel (default), 1 = literal, 2 = warp-per-row interval refinement
     // search workspace (mutable state of the last search on this map)
@@ -380,12 +381,14 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     const size_t n_px = (size_t)D * dm.plane_elems;
     CUDA_TRY(m->planes.reserve(n_px * sizeof(float)));
     CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t)));
-    const bool band_path = m->exact && m->params.distance != FDCM_L1 && m->row_mode == 0;
-    if (m->exact && !band_path) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
-    if (band_path) {
-        CUDA_TRY(m->band_info.reserve(dt_band_info_bytes(dm)));
-        CUDA_TRY(m->band_spill.reserve(dt_band_spill_bytes(dm, m->col_hi - m->col_lo + 1)));
-    }
+    const bool band_ok = m->row_mode == 0 && dt_band_smem_bytes(dm) <= 200 * 1024;
+    const bool band_path = m->exact && m->params.distance != FDCM_L1 && band_ok;     // L2 / L2^2, exact regime
+    const bool band_l1 = m->params.distance == FDCM_L1 && band_ok;                    // L1, any size
+    m->band_path = band_path;
+    m->band_l1 = band_l1;
+    if (m->exact && !band_path && !band_l1) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
+    if (band_path || band_l1) CUDA_TRY(m->band_info.reserve(dt_band_info_bytes(dm)));
+    if (band_path) CUDA_TRY(m->band_spill.reserve(dt_band_spill_bytes(dm, m->col_hi - m->col_lo + 1)));
     if (m->params.distance != FDCM_L1 && !band_path) CUDA_TRY(m->stack.reserve(n_px * 8));
     CUDA_TRY(m->rtab.reserve((size_t)D * std::max(dm.W, dm.H) * sizeof(int32_t)));
     CUDA_TRY(m->lines.reserve((size_t)n_lines * 16));
@@ -415,7 +418,20 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
     }
     const int dist = m->params.distance;
     bool fused_propagate = false;
-    if (m->exact && dist != FDCM_L1 && m->row_mode == 0) {
+    if (m->band_l1) {
+        {
+            KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
+            launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, s);
+        }
+        fused_propagate = m->stage != 1 && m->fuse_fill && dt_fill_propagate_supported(dm);
+        if (fused_propagate) {
+            KernelScope k("dt_l1_propagate", (double)dt_band_info_bytes(dm) + N, s);
+            launch_dt_l1_propagate(m->band_info.p, m->planes.as<float>(), dm, m->prop, s);
+        } else {
+            KernelScope k("dt_row_l1_band", (double)dt_band_info_bytes(dm) + N, s);
+            launch_dt_row_l1_band(m->band_info.p, m->planes.as<float>(), dm, s);
+        }
+    } else if (m->band_path) {
         {
             KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
             launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, s);

@@ -30,6 +30,11 @@ bool dt_fill_propagate_supported(const MapDims& dm);
 void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,
                               bool sqrt_first, cudaStream_t s);
 
+// L1: row call straight from the band records (exact at any size), stand-alone or fused with propagateOrientation
+void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& dm, cudaStream_t s);
+void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& dm, const PropParams& pp, cudaStream_t s);
+size_t dt_band_smem_bytes(const MapDims& dm);
+
 // ---- search_kernels.cu ----
 struct MapView {                 // read-only view of a built feature map
     const float* planes;
