@@ -576,12 +576,14 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
                                                           const __grid_constant__ SceneView sv,
                                                           const __grid_constant__ SearchLaunch sl,
                                                           const __grid_constant__ SearchOutputs out) {
-    extern __shared__ uint8_t s_bins[];   // [warp of the block][line]
+    extern __shared__ __align__(16) uint8_t s_raw[];   // per warp: aligned end points float4[max_lines], planes u8[max_lines]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long slot_idx = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
     if (slot_idx >= sl.n_hyp) return;     // whole warp
     const long long h = sl.perm ? (long long)sl.perm[slot_idx] : slot_idx;
-    uint8_t* bins = s_bins + (size_t)warp * tv.max_lines;
+    const size_t per_warp = (size_t)tv.max_lines * 16 + (((size_t)tv.max_lines + 15) & ~(size_t)15);
+    float4* apts = reinterpret_cast<float4*>(s_raw + (size_t)warp * per_warp);   // transform(T, line) (core/math.h:341-344)
+    uint8_t* bins = reinterpret_cast<uint8_t*>(apts + tv.max_lines);
     unsigned long long n_eval = 0;
     bool valid = false;
 
@@ -617,6 +619,7 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
             xform(T, p.z, p.w, bx, by);
             mnx = fminf(mnx, fminf(ax, bx)); mxx = fmaxf(mxx, fmaxf(ax, bx));
             mny = fminf(mny, fminf(ay, by)); mxy = fmaxf(mxy, fmaxf(ay, by));
+            apts[i] = make_float4(ax, ay, bx, by);     // the aligned template: identical for every candidate translation
             bins[i] = (uint8_t)bin_of_slope_dev(table, (by - ay) / (bx - ax));
         }
 #pragma unroll
@@ -631,7 +634,7 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
         if (isfinite(min_mul) && isfinite(max_mul)) {
             const float* planes = map.planes;
             const unsigned pitch = (unsigned)map.dm.pitch;
-            const int Wm1 = map.dm.W - 1, Hm1 = map.dm.H - 1;
+            const unsigned last = (unsigned)(map.dm.plane_elems - 1);
             // (long) conversions of batchoptimize.cpp:51,74; |multiplier| < map side <= 65534, so int arithmetic is exact
             const int maxm = (int)min(max(trunc_ll(max_mul), -70000LL), 70000LL), minm = (int)min(max(trunc_ll(min_mul), -70000LL), 70000LL);
             // score of multiplier m on this lane (dt3cpu.cpp:126-179)
@@ -639,15 +642,12 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
                 const float m = (float)mult;
                 const float offx = map.shift_x + m * svx, offy = map.shift_y + m * svy;   // sceneTranslation + translation
                 return eigen_sum_lazy(L, [&](int i) {
-                    const float4 p = __ldg(TL + i);
-                    float ax, ay, bx, by;
-                    xform(T, p.x, p.y, ax, ay);
-                    xform(T, p.z, p.w, bx, by);
-                    int x1 = (int)(ax + offx), y1 = (int)(ay + offy), x2 = (int)(bx + offx), y2 = (int)(by + offy);
-                    x1 = min(max(x1, 0), Wm1); x2 = min(max(x2, 0), Wm1);   // guards only (no-ops inside the
-                    y1 = min(max(y1, 0), Hm1); y2 = min(max(y2, 0), Hm1);   // minmaxTranslation bounds)
+                    const float4 a = apts[i];
+                    const int x1 = (int)(a.x + offx), y1 = (int)(a.y + offy), x2 = (int)(a.z + offx), y2 = (int)(a.w + offy);
+                    // inside the minmaxTranslation bounds every index is in range; the clamp only guards non-finite input
+                    const unsigned i1 = min((unsigned)y1 * pitch + (unsigned)x1, last), i2 = min((unsigned)y2 * pitch + (unsigned)x2, last);
                     const float* P = planes + (size_t)bins[i] * map.dm.plane_elems;
-                    return fabsf(__ldg(P + ((unsigned)y1 * pitch + (unsigned)x1)) - __ldg(P + ((unsigned)y2 * pitch + (unsigned)x2)));
+                    return fabsf(__ldg(P + i1) - __ldg(P + i2));
                 });
             };
             // cached range of scores: lane l holds the score of multiplier c_lo + l, l < c_n
@@ -748,7 +748,7 @@ void launch_search(const MapView& map, const SlopeTableDev& table, const Templat
         return;
     }
     const int threads = 128, hyps = threads / 32;
-    const size_t smem = (size_t)hyps * tv.max_lines;
+    const size_t smem = (size_t)hyps * ((size_t)tv.max_lines * 16 + (((size_t)tv.max_lines + 15) & ~(size_t)15));
     if (smem > 48 * 1024) cudaFuncSetAttribute(search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned grid = (unsigned)((sl.n_hyp + hyps - 1) / hyps);
     search_warp_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
