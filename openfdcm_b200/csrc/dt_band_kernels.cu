@@ -83,7 +83,6 @@ __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __rest
 // row call, one lane per row
 // =============================================================================================
 constexpr int kRing = 32;                       // stack entries below the top kept in shared memory, per row
-constexpr int kBandWarps = 2;                   // warps (= bands) per CTA
 
 // stack entry: x = f(v) + v^2, y = v | (first owned pixel) << 16
 __device__ __forceinline__ void sts_u64(uint32_t addr, uint2 v) {
@@ -103,23 +102,36 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // The envelope stack of one row: top entry in registers, the kRing entries below it in a shared-memory ring (this
 // lane's column of [kRing][32] 8-byte slots), older ones in the row's global array (a sequential walk stays inside
 // one 128-byte line for 16 entries, so only one access in 16 pays the L2 latency).
+// Two stacks per row: the LEFT one takes the columns below the split in ascending order and stores for every vertex the
+// first pixel it owns; the RIGHT one takes the columns from the split on in DESCENDING order (mirror image: stores the
+// last pixel a vertex owns).  The left stack grows from the front of the row's array, the right one from its back, so
+// that afterwards the array reads in ascending vertex order: [0, K_left) and [maxdepth - K_right, maxdepth).
 struct RowStack {
     uint32_t ring0;         // shared address of this lane's slot 0
     uint32_t so;            // byte offset of slot (k & (kRing-1)): where entry k goes when it is displaced from the registers
-    uint2* spill;
+    uint2* spill;           // entry k lives at spill[sdir * k]
+    int sdir;
     int k, cnt;             // index of the top entry; the ring holds entries [k - cnt, k - 1]
     uint32_t topkey, topvs;
-    int topv, tops;
-    __device__ __forceinline__ void push(int v, int start, uint32_t key) {
+    int topv, tops;         // vertex and first (left stack) / last (right stack) owned pixel of the top
+
+    __device__ __forceinline__ void init(uint32_t ring_addr, uint2* slot0, int dir) {
+        ring0 = ring_addr;
+        so = (kRing - 1) * 256u;
+        spill = slot0;
+        sdir = dir;
+        k = -1; cnt = 0; topkey = 0; topvs = 0; topv = 0; tops = 0;
+    }
+    __device__ __forceinline__ void push(int v, int bound, uint32_t key) {
         if (k >= 0) {
-            if (cnt == kRing) spill[k - kRing] = lds_u64(ring0 + so);   // ring full: its oldest entry (same slot) leaves
+            if (cnt == kRing) spill[sdir * (k - kRing)] = lds_u64(ring0 + so);   // ring full: its oldest entry (same slot) leaves
             else ++cnt;
             sts_u64(ring0 + so, make_uint2(topkey, topvs));
         }
         ++k;
         so = (so + 256u) & (kRing * 256u - 1u);
-        topv = v; tops = start; topkey = key;
-        topvs = (uint32_t)v | ((uint32_t)start << 16);
+        topv = v; tops = bound; topkey = key;
+        topvs = (uint32_t)v | ((uint32_t)bound << 16);
     }
     __device__ __forceinline__ void pop() {
         --k;
@@ -130,68 +142,98 @@ struct RowStack {
             --cnt;
             e = lds_u64(ring0 + so);
         } else {
-            e = spill[k];
+            e = spill[sdir * k];
         }
         topkey = e.x;
         topvs = e.y;
         topv = (int)(e.y & 0xFFFFu);
         tops = (int)(e.y >> 16);
     }
-    // one column: parabola (v, key = g^2 + v^2) against the envelope so far (imgproc.h:104-120 on integers)
-    __device__ __forceinline__ void column(int v, int gv, int Wm1) {
-        const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
-        int start = 0;
+    // floor(N / Dn) for 0 <= N / Dn < 2897: the biased approximate quotient is below the true one by less than 0.003
+    static __device__ __forceinline__ int floor_div(int N, int Dn) {
+        const float qf = __fmaf_rn((float)N, rcp_approx((float)Dn), -0.002f);
+        const int t = __float2int_rd(qf);        // floor(N / Dn) or one less
+        return t + ((N - t * Dn) >= Dn ? 1 : 0);
+    }
+    // first pixel from which parabola (v, key), v right of every vertex of the stack, beats the envelope (imgproc.h:
+    // 104-120 on integers; the left parabola keeps ties); pops the vertices that end up owning nothing; >= W: never
+    __device__ __forceinline__ int take_over(int v, uint32_t key, int Wm1) {
         while (k >= 0) {
-            // v beats the top strictly from pixel floor(N / Dn) + 1 on (the left parabola keeps ties)
             const int N = (int)key - (int)topkey;
             const int Dn = 2 * (v - topv);
-            if (N < tops * Dn) {                 // ... not after the top's first pixel: the top owns nothing
+            if (N < tops * Dn) {                 // from a pixel not after the top's first one: the top owns nothing
                 pop();
                 continue;
             }
-            if (N >= Wm1 * Dn) return;           // ... beyond the last pixel of the row: v never owns anything
-            // 0 <= N / Dn < W - 1 <= 2896: the biased approximate quotient is below the true one by less than 0.003
-            const float qf = __fmaf_rn((float)N, rcp_approx((float)Dn), -0.002f);
-            const int t = __float2int_rd(qf);    // floor(N / Dn) or one less
-            start = t + 1 + ((N - t * Dn) >= Dn ? 1 : 0);
+            if (N >= Wm1 * Dn) return Wm1 + 1;   // beyond the last pixel of the row
+            return floor_div(N, Dn) + 1;
+        }
+        return 0;
+    }
+    // left stack, one column: ascending v
+    __device__ __forceinline__ void column(int v, int gv, int Wm1) {
+        const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
+        const int start = take_over(v, key, Wm1);
+        if (start <= Wm1) push(v, start, key);
+    }
+    // right stack, one column: descending v.  Parabola v (left of every vertex of the stack) is not worse than the top up
+    // to pixel floor(N / Dn) (it keeps ties); the top is popped when that reaches the top's last pixel.
+    __device__ __forceinline__ void column_rev(int v, int gv, int Wm1) {
+        const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
+        int end = Wm1;
+        while (k >= 0) {
+            const int N = (int)topkey - (int)key;
+            const int Dn = 2 * (topv - v);
+            if (N >= tops * Dn) {
+                pop();
+                continue;
+            }
+            if (N < 0) return;                   // not even pixel 0: v never owns anything
+            end = floor_div(N, Dn);
             break;
         }
-        push(v, start, key);
+        push(v, end, key);
     }
+    // write the ring and the top to the global array; returns the number of entries
+    __device__ __forceinline__ int park() {
+        if (k >= 0) {
+            for (int i = k - cnt; i < k; ++i) spill[sdir * i] = lds_u64(ring0 + (uint32_t)(i & (kRing - 1)) * 256u);
+            spill[sdir * k] = make_uint2(topkey, topvs);
+        }
+        return k + 1;
+    }
+};
+
+// per-row result of the envelope kernel
+struct RowMeta {
+    int32_t k_left;         // entries [0, k_left) of the row array, {f(v) + v^2, v | first owned pixel << 16}
+    int32_t k_right;        // entries [maxdepth - k_right, maxdepth), {f(v) + v^2, v | LAST owned pixel << 16}
+    int32_t right_start;    // first pixel of the first right entry (the following ones start after their predecessor's last)
+    int32_t pad;
 };
 
 // kFromG = false: g is derived from the band records of dt_col_band_kernel (product path).
 // kFromG = true : g rows are given explicitly (u16, 0xFFFF = FLT_MAX), any content (row-pass parity tests).
+// One CTA of two warps per band, lane = row: warp 0 builds the left stack over the columns [0, xsplit), warp 1 the right
+// stack over [xsplit, W) from the right; warp 0 then joins them: the right entries are offered to the left stack in
+// ascending order until one keeps a pixel (the lower envelopes of two column ranges cross exactly once).  The serial
+// chain per row is half as long as with one stack and twice as many warps are in flight.
 // Workspace rows are padded to 32 per band (row id = (d * nbands + b) * 32 + lane) so that the rows past H of the last
 // band need no special case: they build an envelope nobody reads.
-template <bool kFromG>
-__global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint2* __restrict__ info,
-                                                                      const uint16_t* __restrict__ g, MapDims dm, int nbands,
-                                                                      uint2* __restrict__ spill_all, int maxdepth,
-                                                                      int32_t* __restrict__ row_k) {
-    __shared__ __align__(16) uint2 ring_all[kBandWarps][kRing * 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wg = blockIdx.x * kBandWarps + warp;          // band id, plane-fastest (neighbouring warps: different planes)
-    if (wg >= dm.D * nbands) return;
-    const int d = wg % dm.D, b = wg / dm.D;
-    const int row0 = b * 32;
+template <bool kFromG, bool kRev>
+__device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restrict__ info_row, const uint16_t* __restrict__ g,
+                                              const uint16_t* __restrict__ g_row, const MapDims& dm, int d, int row0, int x_begin,
+                                              int x_end, int lane) {
     const int W = dm.W, Wm1 = dm.W - 1;
-    const uint2* info_row = info + ((size_t)d * nbands + b) * dm.pitch + lane;
-    const uint16_t* g_row = kFromG ? g + ((size_t)d * dm.H + min(row0 + lane, dm.H - 1)) * dm.pitch : nullptr;
-    const size_t prow = ((size_t)d * nbands + b) * 32 + lane;
-
-    RowStack st;
-    st.ring0 = (uint32_t)__cvta_generic_to_shared(ring_all[warp]) + (uint32_t)lane * 8u;
-    st.so = (kRing - 1) * 256u;
-    st.spill = spill_all + prow * maxdepth;
-    st.k = -1; st.cnt = 0; st.topkey = 0; st.topvs = 0; st.topv = 0; st.tops = 0;
     const uint32_t mle = 0xFFFFFFFFu >> (31 - lane), mge = 0xFFFFFFFFu << lane;
     const int l31 = 31 - lane;
-
-    // ---- lower envelope over the columns that hold a finite g (imgproc.h:101-121) ----
-    uint2 e_next = make_uint2(0u, 0xFFFFFFFFu);
-    if (!kFromG && lane < W) e_next = info_row[0];
-    for (int x0 = 0; x0 < dm.pitch; x0 += 32) {
+    const uint2 kNone = make_uint2(0u, 0xFFFFFFFFu);
+    const int nchunks = (x_end - x_begin) >> 5;
+    auto chunk_x0 = [&](int c) { return kRev ? x_end - 32 * (c + 1) : x_begin + 32 * c; };
+    uint2 e_next = kNone;
+    if (!kFromG && nchunks > 0 && chunk_x0(0) + lane < W) e_next = info_row[chunk_x0(0)];
+    for (int c = 0; c < nchunks; ++c) {
+        const int x0 = chunk_x0(c);
         const uint2 e = e_next;
         unsigned todo;
         if (kFromG) {
@@ -201,46 +243,87 @@ __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint
                 if (g[((size_t)d * dm.H + row0 + r) * dm.pitch + x0 + lane] != kNone16) any = 1;
             todo = __ballot_sync(0xffffffffu, any && x0 + lane < W);
         } else {
-            e_next = make_uint2(0u, 0xFFFFFFFFu);
-            if (x0 + 32 + lane < W) e_next = info_row[x0 + 32];           // next chunk's records, one iteration ahead
+            e_next = kNone;
+            if (c + 1 < nchunks && chunk_x0(c + 1) + lane < W) e_next = info_row[chunk_x0(c + 1)];   // one iteration ahead
             todo = __ballot_sync(0xffffffffu, e.x != 0u || e.y != 0xFFFFFFFFu);
         }
-        if (kFromG) {
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
-                const int gv = g_row[x0 + j];
-                if (row0 + lane < dm.H && gv != (int)kNone16) st.column(x0 + j, gv, Wm1);
-            }
-        } else if (__ballot_sync(0xffffffffu, e.x != 0u) == 0u) {
-            // no edge pixel inside the band in these 32 columns: g = distance to the nearest edge above / below the band
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
+        const bool no_bits = kFromG || __ballot_sync(0xffffffffu, e.x != 0u) == 0u;   // no edge pixel inside the band here
+        while (todo) {
+            const int j = kRev ? 31 - __clz(todo) : __ffs(todo) - 1;
+            todo &= ~(1u << j);
+            int gv;
+            bool fin = true;
+            if (kFromG) {
+                gv = g_row[x0 + j];
+                fin = row0 + lane < dm.H && gv != (int)kNone16;
+            } else if (no_bits) {
+                // g = distance to the nearest edge above / below the band
                 const uint32_t ud = __shfl_sync(0xffffffffu, e.y, j);
-                const int gv = min(lane + (int)(ud & 0xFFFFu), l31 + (int)(ud >> 16));
-                st.column(x0 + j, gv, Wm1);
-            }
-        } else {
-            while (todo) {
-                const int j = __ffs(todo) - 1;
-                todo &= todo - 1;
+                gv = min(lane + (int)(ud & 0xFFFFu), l31 + (int)(ud >> 16));
+            } else {
                 const uint32_t M = __shfl_sync(0xffffffffu, e.x, j), ud = __shfl_sync(0xffffffffu, e.y, j);
                 const uint32_t above = M & mle, below = M & mge;
                 const int ua = __clz(above) - 31, ub = (int)(ud & 0xFFFFu);       // lane - (row of the last edge at or above)
                 const int da = __ffs(below) - 1 - 31, db = (int)(ud >> 16);       // (row of the first edge at or below) - 31
-                const int gv = min(lane + (above ? ua : ub), l31 + (below ? da : db));
-                st.column(x0 + j, gv, Wm1);
+                gv = min(lane + (above ? ua : ub), l31 + (below ? da : db));
+            }
+            if (fin) {
+                if (kRev) st.column_rev(x0 + j, gv, Wm1);
+                else st.column(x0 + j, gv, Wm1);
             }
         }
     }
-    // ---- park the whole stack in the row's global array; the fill kernel walks it ----
-    const int K = st.k + 1;
-    if (K > 0) {
-        for (int i = st.k - st.cnt; i < st.k; ++i) st.spill[i] = lds_u64(st.ring0 + (uint32_t)(i & (kRing - 1)) * 256u);
-        st.spill[st.k] = make_uint2(st.topkey, st.topvs);
+}
+
+template <bool kFromG>
+__global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict__ info, const uint16_t* __restrict__ g, MapDims dm,
+                                                         int nbands, uint2* __restrict__ spill_all, int maxdepth,
+                                                         RowMeta* __restrict__ row_meta, int xsplit) {
+    __shared__ __align__(16) uint2 ring_all[2][kRing * 32];
+    __shared__ int s_kright[32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wg = blockIdx.x;                              // band id, plane-fastest (neighbouring CTAs: different planes)
+    const int d = wg % dm.D, b = wg / dm.D;
+    const int row0 = b * 32;
+    const int Wm1 = dm.W - 1;
+    const uint2* info_row = info + ((size_t)d * nbands + b) * dm.pitch + lane;
+    const uint16_t* g_row = kFromG ? g + ((size_t)d * dm.H + min(row0 + lane, dm.H - 1)) * dm.pitch : nullptr;
+    const size_t prow = ((size_t)d * nbands + b) * 32 + lane;
+    uint2* row_entries = spill_all + prow * maxdepth;
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring_all[warp]) + (uint32_t)lane * 8u;
+
+    RowStack st;
+    if (warp == 1) {
+        st.init(ring_addr, row_entries + (maxdepth - 1), -1);
+        envelope_half<kFromG, true>(st, info_row, g, g_row, dm, d, row0, xsplit, dm.pitch, lane);
+        s_kright[lane] = st.park();
+    } else {
+        st.init(ring_addr, row_entries, 1);
+        envelope_half<kFromG, false>(st, info_row, g, g_row, dm, d, row0, 0, xsplit, lane);
     }
-    row_k[prow] = K;
+    __syncthreads();
+    if (warp != 0) return;
+    // ---- join: offer the right entries (ascending vertex) to the left stack until one keeps a pixel ----
+    const int k_right = s_kright[lane];
+    const uint2* right = row_entries + (maxdepth - k_right);
+    int j = 0, right_start = 0;
+    while (j < k_right) {
+        const uint2 r = right[j];
+        ++j;
+        const int v = (int)(r.y & 0xFFFFu), end = (int)(r.y >> 16);
+        const int start = st.take_over(v, r.x, Wm1);
+        if (start <= end) {                      // it owns [start, end]: it becomes the top of the left stack
+            st.push(v, start, r.x);
+            right_start = end + 1;
+            break;
+        }
+    }
+    RowMeta meta;
+    meta.k_left = st.park();
+    meta.k_right = k_right - j;
+    meta.right_start = right_start;
+    meta.pad = 0;
+    row_meta[prow] = meta;
 }
 
 // =============================================================================================
@@ -256,26 +339,35 @@ __global__ void __launch_bounds__(kBandWarps * 32) dt_row_band_kernel(const uint
 //   popc(marks & bits <= p)-th of them (or the entry carried over from the left).
 // =============================================================================================
 struct RowFill {
-    const uint2* row;       // the row's entries
-    const uint2* sp;        // this lane's slot of the current 32-entry batch: row + e0 + lane
+    const uint2* row;       // the row's array: left entries at the front, right entries at the back (see RowMeta)
+    int KL, roff, rstart;   // left entries; array slot of right entry i is i + roff; first pixel of the first right entry
     int K, e0, ci, nxt;     // entries; first entry of the batch; entries consumed; first pixel of entry ci (uniform)
     uint2 be, nbe, pbe;     // batch entry of this lane (x = resolved base), same lane of the next (raw) / previous (resolved) batch
     int carry_v;            // the entry that owns the pixel left of the current chunk (uniform)
     uint32_t carry_b;
 
+    // entry i of the joined envelope as {f(v) + v^2, v | first owned pixel << 16}
+    __device__ __forceinline__ uint2 entry(int i) const {
+        if (i < KL) return row[i];
+        uint2 e = row[i + roff];
+        const uint32_t start = i == KL ? (uint32_t)rstart : (row[i + roff - 1].y >> 16) + 1u;   // predecessor's last pixel + 1
+        e.y = (e.y & 0xFFFFu) | (start << 16);
+        return e;
+    }
+    __device__ __forceinline__ uint2 batch_entry(int i) const { return i < K ? entry(i) : make_uint2(0u, 0xFFFFFFFFu); }
     __device__ uint32_t slow_base(int idx) const {
         uint32_t acc = 0;
         int cur = idx;
         while (true) {
-            const uint2 e = row[cur];
+            const uint2 e = entry(cur);
             const int v = (int)(e.y & 0xFFFFu), s = (int)(e.y >> 16);
             if (s <= v) return e.x - (uint32_t)(v * v) + acc;
             int lo = 0, hi = cur - 1;            // largest o with s_o <= v (s_0 = 0)
             while (lo < hi) {
                 const int mid = (lo + hi + 1) >> 1;
-                if ((int)(row[mid].y >> 16) <= v) lo = mid; else hi = mid - 1;
+                if ((int)(entry(mid).y >> 16) <= v) lo = mid; else hi = mid - 1;
             }
-            const int dd = v - (int)(row[lo].y & 0xFFFFu);
+            const int dd = v - (int)(entry(lo).y & 0xFFFFu);
             acc += (uint32_t)(dd * dd);
             cur = lo;
         }
@@ -337,14 +429,15 @@ struct RowFill {
         }
         be.x = base;
     }
-    __device__ __forceinline__ void init(const uint2* row_entries, int k, int lane) {
-        const uint2 kSentinel = make_uint2(0u, 0xFFFFFFFFu);   // s = 0xFFFF: never starts inside a chunk
+    __device__ __forceinline__ void init(const uint2* row_entries, const RowMeta meta, int maxdepth, int lane) {
         row = row_entries;
-        sp = row_entries + lane;
-        K = k; e0 = 0; ci = 0; nxt = k > 0 ? 0 : 0x7FFFFFFF;
-        be = lane < K ? sp[0] : kSentinel;
-        nbe = 32 + lane < K ? sp[32] : kSentinel;
-        pbe = kSentinel;
+        KL = meta.k_left;
+        roff = maxdepth - meta.k_right - meta.k_left;
+        rstart = meta.right_start;
+        K = meta.k_left + meta.k_right; e0 = 0; ci = 0; nxt = K > 0 ? 0 : 0x7FFFFFFF;
+        be = batch_entry(lane);              // (sentinel s = 0xFFFF: never starts inside a chunk)
+        nbe = batch_entry(32 + lane);
+        pbe = make_uint2(0u, 0xFFFFFFFFu);
         carry_v = 0; carry_b = 0;
         resolve(lane);
     }
@@ -355,10 +448,9 @@ struct RowFill {
         while (nxt < q0 + 32) {                               // some interval starts inside this chunk
             if (ci == e0 + 32) {                              // ... in the next 32 entries
                 e0 += 32;
-                sp += 32;
                 pbe = be;
                 be = nbe;
-                nbe = e0 + 32 + lane < K ? sp[32] : make_uint2(0u, 0xFFFFFFFFu);
+                nbe = batch_entry(e0 + 32 + lane);
                 resolve(lane);
             }
             const int bv = (int)(be.y & 0xFFFFu);
@@ -392,7 +484,7 @@ __device__ __forceinline__ size_t padded_row(int row, int H) {   // [D*H] row id
 
 // stand-alone fill (stage-wise builds, depths without a fused kernel): one warp per row
 __global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint2* __restrict__ spill_all,
-                                                                      const int32_t* __restrict__ row_k,
+                                                                      const RowMeta* __restrict__ row_meta,
                                                                       float* __restrict__ planes, MapDims dm, int n_rows_total,
                                                                       int maxdepth) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -401,13 +493,13 @@ __global__ void __launch_bounds__(kFillWarps * 32) dt_row_fill_kernel(const uint
     const int W = dm.W;
     float* op = planes + (size_t)row * dm.pitch + lane;       // this lane's pixel of the current chunk
     const size_t prow = padded_row(row, dm.H);
-    const int K = row_k[prow];
-    if (K <= 0) {                                             // no edge pixel in this plane: FLT_MAX stays (imgproc.h:174)
+    const RowMeta meta = row_meta[prow];
+    if (meta.k_left + meta.k_right <= 0) {                    // no edge pixel in this plane: FLT_MAX stays (imgproc.h:174)
         for (int q = lane; q < W; q += 32, op += 32) *op = FLT_MAX;
         return;
     }
     RowFill rf;
-    rf.init(spill_all + prow * maxdepth, K, lane);
+    rf.init(spill_all + prow * maxdepth, meta, maxdepth, lane);
     const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
     for (int q0 = 0; q0 < dm.pitch; q0 += 32, op += 32) {
         const uint32_t val = rf.chunk(q0, lane, le_mask);
@@ -470,7 +562,7 @@ __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int ch
 
 template <int D>
 __global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
-dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const int32_t* __restrict__ row_k, float* __restrict__ planes,
+dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
                          MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first) {
     using C = FPConfig<D>;
     extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] squared distances (0xFFFFFFFF: FLT_MAX)
@@ -485,8 +577,9 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const int32_t* __r
         Kp[p] = 0;
         if (d < D) {
             const size_t prow = (size_t)d * Hp + y;
-            Kp[p] = row_k[prow];
-            rf[p].init(spill_all + prow * maxdepth, Kp[p], lane);
+            const RowMeta meta = row_meta[prow];
+            Kp[p] = meta.k_left + meta.k_right;
+            rf[p].init(spill_all + prow * maxdepth, meta, maxdepth, lane);
         }
     }
     const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
@@ -638,8 +731,8 @@ static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1
 int dt_band_count(const MapDims& dm) { return (dm.H + 31) / 32; }
 size_t dt_band_info_bytes(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * dm.pitch * sizeof(uint2); }
 static size_t padded_rows(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * 32; }
-static size_t row_k_bytes(const MapDims& dm) { return (padded_rows(dm) * sizeof(int32_t) + 255) / 256 * 256; }
-// workspace of the row call: per-row envelope length + per-row envelope array of maxdepth entries
+static size_t row_k_bytes(const MapDims& dm) { return (padded_rows(dm) * sizeof(RowMeta) + 255) / 256 * 256; }
+// workspace of the row call: per-row RowMeta + per-row envelope array of maxdepth entries
 size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth) {
     return row_k_bytes(dm) + padded_rows(dm) * (size_t)maxdepth * sizeof(uint2);
 }
@@ -657,12 +750,12 @@ void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info,
 }
 
 // [win_lo, win_hi]: columns that can hold an edge pixel (envelope vertices only exist there)
-struct RowWs { int32_t* row_k; uint2* spill; int win_lo, maxdepth; };
+struct RowWs { RowMeta* row_k; uint2* spill; int win_lo, maxdepth; };
 static RowWs row_ws(const MapDims& dm, void* d_ws, int win_lo, int win_hi) {
     win_lo = win_lo < 0 ? 0 : win_lo;
     win_hi = win_hi >= dm.W ? dm.W - 1 : win_hi;
     if (win_hi < win_lo) { win_lo = 0; win_hi = dm.W - 1; }
-    return RowWs{reinterpret_cast<int32_t*>(d_ws), reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(d_ws) + row_k_bytes(dm)),
+    return RowWs{reinterpret_cast<RowMeta*>(d_ws), reinterpret_cast<uint2*>(reinterpret_cast<unsigned char*>(d_ws) + row_k_bytes(dm)),
                  win_lo, win_hi - win_lo + 1};
 }
 
@@ -670,12 +763,14 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
                             cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int nbands = dt_band_count(dm);
-    const unsigned grid = cdiv_u((size_t)dm.D * nbands, kBandWarps);
+    const unsigned grid = (unsigned)(dm.D * nbands);
+    // split column: middle of the window that can hold edge pixels, on a 32-column boundary
+    const int xsplit = min(dm.pitch, max(0, ((ws.win_lo + ws.win_lo + ws.maxdepth) / 2) & ~31));
     if (d_g)
-        dt_row_band_kernel<true><<<grid, kBandWarps * 32, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k);
+        dt_row_band_kernel<true><<<grid, 64, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit);
     else
-        dt_row_band_kernel<false><<<grid, kBandWarps * 32, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands, ws.spill,
-                                                                  ws.maxdepth, ws.row_k);
+        dt_row_band_kernel<false><<<grid, 64, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands, ws.spill, ws.maxdepth,
+                                                     ws.row_k, xsplit);
 }
 
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
