@@ -343,6 +343,7 @@ struct RowFill {
     int KL, roff, rstart;   // left entries; array slot of right entry i is i + roff; first pixel of the first right entry
     int K, e0, ci, nxt;     // entries; first entry of the batch; entries consumed; first pixel of entry ci (uniform)
     uint2 be, nbe, pbe;     // batch entry of this lane (x = resolved base), same lane of the next (raw) / previous (resolved) batch
+    uint32_t raw_last;      // stored second field (first / last pixel) of the last lane of the current batch (uniform)
     int carry_v;            // the entry that owns the pixel left of the current chunk (uniform)
     uint32_t carry_b;
 
@@ -354,7 +355,17 @@ struct RowFill {
         e.y = (e.y & 0xFFFFu) | (start << 16);
         return e;
     }
-    __device__ __forceinline__ uint2 batch_entry(int i) const { return i < K ? entry(i) : make_uint2(0u, 0xFFFFFFFFu); }
+    // batch loading: one raw load per lane; the right entries get their first pixel from the lane below (the last pixel
+    // of the predecessor, + 1), lane 0 from the last lane of the previous batch
+    __device__ __forceinline__ uint2 load_raw(int i) const { return i < K ? row[i < KL ? i : i + roff] : make_uint2(0u, 0xFFFFFFFFu); }
+    __device__ __forceinline__ uint2 convert(uint2 raw, int i, int lane, uint32_t prev_last) const {
+        const uint32_t below = __shfl_up_sync(0xffffffffu, raw.y >> 16, 1);
+        if (i >= KL && i < K) {
+            const uint32_t start = i == KL ? (uint32_t)rstart : (lane ? below : prev_last) + 1u;
+            raw.y = (raw.y & 0xFFFFu) | (start << 16);
+        }
+        return raw;
+    }
     __device__ uint32_t slow_base(int idx) const {
         uint32_t acc = 0;
         int cur = idx;
@@ -435,8 +446,10 @@ struct RowFill {
         roff = maxdepth - meta.k_right - meta.k_left;
         rstart = meta.right_start;
         K = meta.k_left + meta.k_right; e0 = 0; ci = 0; nxt = K > 0 ? 0 : 0x7FFFFFFF;
-        be = batch_entry(lane);              // (sentinel s = 0xFFFF: never starts inside a chunk)
-        nbe = batch_entry(32 + lane);
+        const uint2 raw = load_raw(lane);    // (sentinel s = 0xFFFF: never starts inside a chunk)
+        raw_last = __shfl_sync(0xffffffffu, raw.y >> 16, 31);
+        be = convert(raw, lane, lane, 0u);
+        nbe = load_raw(32 + lane);           // raw: converted when it becomes the current batch
         pbe = make_uint2(0u, 0xFFFFFFFFu);
         carry_v = 0; carry_b = 0;
         resolve(lane);
@@ -449,8 +462,10 @@ struct RowFill {
             if (ci == e0 + 32) {                              // ... in the next 32 entries
                 e0 += 32;
                 pbe = be;
-                be = nbe;
-                nbe = batch_entry(e0 + 32 + lane);
+                const uint32_t prev_last = raw_last;
+                raw_last = __shfl_sync(0xffffffffu, nbe.y >> 16, 31);
+                be = convert(nbe, e0 + lane, lane, prev_last);
+                nbe = load_raw(e0 + 32 + lane);
                 resolve(lane);
             }
             const int bv = (int)(be.y & 0xFFFFu);
@@ -469,7 +484,8 @@ struct RowFill {
             ci += __popc(bal);
             if (ci >= K) nxt = 0x7FFFFFFF;
             else if (ci < e0 + 32) nxt = (int)(__shfl_sync(0xffffffffu, be.y, ci - e0) >> 16);
-            else nxt = (int)(__shfl_sync(0xffffffffu, nbe.y, 0) >> 16);
+            else if (ci < KL) nxt = (int)(__shfl_sync(0xffffffffu, nbe.y, 0) >> 16);      // first entry of the next (raw) batch
+            else nxt = ci == KL ? rstart : (int)raw_last + 1;
         }
         const int dq = q0 + lane - ov;
         return ob + (uint32_t)(dq * dq);
