@@ -859,6 +859,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // y-major planes: thread per chain, the row access of a warp is one coalesced 128-byte segment; kYU loads in
 // flight per thread hide the HBM latency (the running sum itself is the only serial dependency).
 constexpr int kYU = 32;
+constexpr int kYPrefetch = 96;          // rows of L2 prefetch distance
 
 __global__ void __launch_bounds__(128) integral_ymajor_kernel(float* __restrict__ planes, MapDims dm,
                                                               const __grid_constant__ IntegralParams ip,
@@ -878,9 +879,21 @@ __global__ void __launch_bounds__(128) integral_ymajor_kernel(float* __restrict_
     float* row = planes + (size_t)d * dm.plane_elems + (ry < 0 ? (size_t)(dm.H - 1) * dm.pitch : 0);
     float acc = 0.f;
     bool have = false;
+    const int lane = threadIdx.x & 31;
+    const int cw = cmin + (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u));   // first chain of the warp
     for (int i0 = 0; i0 < dm.H; i0 += kYU) {
         float a[kYU];
-        const int32_t rl = (i0 + (int)(threadIdx.x & 31) < dm.H) ? __ldg(R + i0 + (threadIdx.x & 31)) : 0x40000000;   // lane k: shift of row i0+k
+        const int32_t rl = (i0 + lane < dm.H) ? __ldg(R + i0 + lane) : 0x40000000;   // lane k: shift of row i0+k
+        {   // pull the rows kYPrefetch ahead into L2: lane k takes row i0 + kYPrefetch + k (the warp's 128-byte segment
+            // of that row starts at chain cw; it may straddle two lines)
+            const int ip = i0 + kYPrefetch + lane;
+            if (ip < dm.H) {
+                const int xp = cw + __ldg(R + ip);
+                const float* rowp = row + (long long)(kYPrefetch + lane) * rstep;
+                if ((unsigned)xp < (unsigned)dm.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + xp));
+                if ((unsigned)(xp + 31) < (unsigned)dm.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + xp + 31));
+            }
+        }
 #pragma unroll
         for (int k = 0; k < kYU; ++k) {
             const int x = c + __shfl_sync(0xffffffffu, rl, k);
