@@ -75,6 +75,20 @@ static fdcm_status get_stream(int device, cudaStream_t* s) {
     return FDCM_OK;
 }
 
+// side stream for host-to-device uploads that may overlap kernels of the main stream (template sets)
+static std::map<int, cudaStream_t> g_copy_streams;
+static fdcm_status get_copy_stream(int device, cudaStream_t* s) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto o = g_copy_streams.find(device);
+    if (o == g_copy_streams.end()) {
+        cudaStream_t ns;
+        CUDA_TRY(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+        o = g_copy_streams.emplace(device, ns).first;
+    }
+    *s = o->second;
+    return FDCM_OK;
+}
+
 extern "C" fdcm_status fdcm_set_stream(int32_t device, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     if (cuda_stream) g_user_streams[device] = (cudaStream_t)cuda_stream;
@@ -226,7 +240,7 @@ struct fdcm_dt3 {
 
     ~fdcm_dt3() {
         cudaSetDevice(device);
-        for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &rtab, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
+        for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &rtab, &band_info, &band_spill, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
                           &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n, &s_keys, &s_keys2, &s_idx,
                           &s_perm, &s_sort_tmp})
             b->release();
@@ -751,8 +765,12 @@ struct fdcm_templates {
     int denom_kind = -1;
     float denom_tau = 0.f;
     std::mutex mu;
+    // uploads run on the copy stream (they overlap a map build in flight on the main stream); consumers wait on `ready`
+    cudaEvent_t ready = nullptr;
+    bool upload_pending = false;
     ~fdcm_templates() {
         cudaSetDevice(device);
+        if (ready) cudaEventDestroy(ready);
         for (DevBuf* b : {&lines, &offs, &argsort, &line_len, &denom}) b->release();
     }
 };
@@ -863,8 +881,23 @@ static void template_host_prep(const float* tl, const int32_t* off, int32_t T, s
 }
 
 // (re)load a template set into an existing object: device buffers grow only, host scratch is reused
+// make the main stream wait for a template upload in flight on the copy stream
+static fdcm_status templates_ready(fdcm_templates* t, cudaStream_t s) {
+    if (t->upload_pending) {
+        CUDA_TRY(cudaStreamWaitEvent(s, t->ready, 0));
+        t->upload_pending = false;
+    }
+    return FDCM_OK;
+}
+
+// Every consumer of a template set is host-synchronous (fdcm_search ends with a stream synchronisation), so no kernel can
+// still be reading the device arrays when they are overwritten here.
 static fdcm_status templates_load(fdcm_templates* t, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
-                                  cudaStream_t s) {
+                                  cudaStream_t main_stream) {
+    (void)main_stream;
+    cudaStream_t s;
+    if (fdcm_status st = get_copy_stream(t->device, &s)) return st;
+    if (!t->ready) CUDA_TRY(cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming));
     if (n_tmpl < 0 || !tmpl_offsets) return fail(FDCM_ERR_INVALID, "bad template offsets");
     for (int i = 0; i < n_tmpl; ++i)
         if (tmpl_offsets[i + 1] < tmpl_offsets[i]) return fail(FDCM_ERR_INVALID, "template offsets must be non-decreasing");
@@ -886,11 +919,12 @@ static fdcm_status templates_load(fdcm_templates* t, const float* tmpl_lines, co
     if (e == cudaSuccess) e = cudaMemcpyAsync(t->offs.p, tmpl_offsets, (size_t)(n_tmpl + 1) * 4, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->argsort.p, t->h_argsort.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess && n) e = cudaMemcpyAsync(t->line_len.p, t->h_line_len.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s);
-    // no synchronisation needed: pageable sources are staged by the runtime before the call returns, and every
-    // consumer runs on the same stream
+    // no host synchronisation needed: pageable sources are staged by the runtime before the call returns
+    if (e == cudaSuccess) e = cudaEventRecord(t->ready, s);
     if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? FDCM_ERR_NOMEM : FDCM_ERR_CUDA,
                     std::string("templates_load: ") + cudaGetErrorString(e));
+    t->upload_pending = true;
     return FDCM_OK;
 }
 
@@ -905,7 +939,8 @@ extern "C" fdcm_status fdcm_templates_create(const float* tmpl_lines, const int3
     if (!t) return fail(FDCM_ERR_NOMEM, "host allocation failed");
     t->device = device;
     fdcm_status st = templates_load(t, tmpl_lines, tmpl_offsets, n_tmpl, s);
-    if (st == FDCM_OK && cudaStreamSynchronize(s) != cudaSuccess) st = fail(FDCM_ERR_CUDA, "templates_create: stream synchronisation failed");
+    if (st == FDCM_OK && cudaEventSynchronize(t->ready) != cudaSuccess) st = fail(FDCM_ERR_CUDA, "templates_create: upload failed");
+    if (st == FDCM_OK) t->upload_pending = false;
     if (st != FDCM_OK) {
         delete t;
         return st;
@@ -967,6 +1002,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t s;
     if (fdcm_status st = get_stream(m->device, &s)) return st;
+    if (fdcm_status st = templates_ready(t, s)) return st;
 
     // ---- host prep: scene length order (defaultsearch.cpp:32-36) and hypothesis offsets ----
     const SceneFilter flt{p->concentric != 0, p->center_x, p->center_y, p->low_radius, p->high_radius};
