@@ -233,6 +233,11 @@ def test_row_pass_exact_kernel_vs_literal_oracle(n):
     rows.append(np.abs(np.arange(n) - n // 3))                 # 45-degree ramp: three-way ties everywhere
     rows.append(np.minimum(np.arange(n) * 3, 2000))            # steep ramp (deep aliasing chains)
     rows.append(np.minimum((np.arange(n)[::-1]) // 2, 2500))   # shallow ramp from the right
+    # finite columns on one side of the split of the two-stack envelope only, and a dense block around it
+    rows.append(np.where(np.arange(n) < max(1, n // 4), rng.integers(0, 60, n), big))
+    rows.append(np.where(np.arange(n) >= n - max(1, n // 4), rng.integers(0, 60, n), big))
+    rows.append(np.where(np.abs(np.arange(n) - n // 2) < 40, rng.integers(0, 9, n), big))
+    rows.append(np.where(np.arange(n) % 2 == 0, 700 - np.arange(n) % 700, big))      # long pops across the split
     for k in range(40):
         r = rng.integers(0, [3, 10, 50, 400, 2800][k % 5], n)
         if k % 3 == 0:
