@@ -690,10 +690,27 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
                     const int jend = min(kk + B - 1, lim);
                     float bmin = 0.f, blast = 0.f;
                     int barg = kk;
-                    for (int j = kk; j <= jend; ++j) {
-                        const float sj = score_at(dir * j, dir);
-                        if (j == kk || sj < bmin) { bmin = sj; barg = j; }   // std::min_element: first minimum
-                        blast = sj;
+                    (void)score_at(dir * kk, dir);                    // makes the cached range start at this batch if needed
+                    const int la = dir * kk - c_lo, lb = dir * jend - c_lo;          // lanes of the first / last candidate
+                    const bool inside = min(la, lb) >= 0 && max(la, lb) < c_n;
+                    const unsigned bmask = inside ? (0xFFFFFFFFu >> (31 - max(la, lb))) & (0xFFFFFFFFu << min(la, lb)) : 0u;
+                    const bool in_batch = (bmask >> lane) & 1u;
+                    // scores are sums of absolute values: non-negative floats order like their bit patterns; NaN (an
+                    // empty plane under a line) takes the sequential path so that `s < bmin` keeps its exact meaning
+                    if (inside && __ballot_sync(0xffffffffu, in_batch && !(c_score >= 0.f)) == 0u) {
+                        const unsigned key = in_batch ? __float_as_uint(c_score) : 0xFFFFFFFFu;
+                        const unsigned kmin = __reduce_min_sync(0xffffffffu, key);
+                        const unsigned hit = __ballot_sync(0xffffffffu, in_batch && key == kmin);
+                        const int lmin = dir > 0 ? __ffs(hit) - 1 : 31 - __clz(hit);   // first minimum in evaluation order
+                        bmin = __uint_as_float(kmin);
+                        barg = dir * (c_lo + lmin);
+                        blast = __shfl_sync(0xffffffffu, c_score, lb);
+                    } else {
+                        for (int j = kk; j <= jend; ++j) {
+                            const float sj = score_at(dir * j, dir);
+                            if (j == kk || sj < bmin) { bmin = sj; barg = j; }   // std::min_element: first minimum
+                            blast = sj;
+                        }
                     }
                     n_eval += (unsigned long long)(jend - kk + 1);
                     if (bmin > back) break;
