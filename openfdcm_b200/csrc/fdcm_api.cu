@@ -1076,6 +1076,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     so.hyp = m->s_hyp.as<int4>();
     so.counters = m->s_counters.as<unsigned long long>();
     sl.perm = nullptr;
+    sl.hyp_ready = nullptr;
     static const bool no_order = [] { const char* e = std::getenv("FDCM_SEARCH_UNORDERED"); return e && e[0] == '1'; }();
     if (!no_order && H >= 4096 && H < (int64_t)1 << 31) {
         // process the hypotheses in the spatial order of their scene lines (L2 locality of the map gathers)
@@ -1092,8 +1093,10 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
         CUDA_TRY(m->s_sort_tmp.reserve(std::max<size_t>(tmp, 16)));
         KernelScope k("search_order", 0.0, s, 1);   // our key kernel; the 3 CUB radix-sort launches are library code
         launch_search_order(tv, sv, sl, m->s_keys.as<uint32_t>(), m->s_keys2.as<uint32_t>(), m->s_idx.as<int32_t>(),
-                            m->s_perm.as<int32_t>(), m->s_sort_tmp.p, tmp, m->s_scene_min[0], m->s_scene_min[1], cells_x, key_bits, s);
+                            m->s_perm.as<int32_t>(), m->s_sort_tmp.p, tmp, m->s_scene_min[0], m->s_scene_min[1], cells_x, key_bits,
+                            so.hyp, s);
         sl.perm = m->s_perm.as<int32_t>();
+        sl.hyp_ready = so.hyp;
     }
     {
         KernelScope k("search", 0.0, s);

@@ -65,6 +65,7 @@ struct SearchLaunch {
     const int64_t* hyp_off;      // n_tmpl + 1 prefix of hypothesis counts
     int64_t n_hyp;
     const int32_t* perm;         // processing order: slot i handles hypothesis perm[i] (nullptr: identity)
+    const int4* hyp_ready;       // hypotheses already decoded by the ordering pass (tmpl + base, tmpl line, scene line, rev)
     const float2* direct_align;  // optimize() entry point: hypothesis h = template h as given (identity transform)
                                  // with alignment vector direct_align[h]; nullptr for the fused search
 };
@@ -80,7 +81,7 @@ struct SearchOutputs {
 size_t search_order_temp_bytes(int64_t n_hyp);
 void launch_search_order(const TemplatesView& tv, const SceneView& sv, const SearchLaunch& sl, uint32_t* d_keys, uint32_t* d_keys_out,
                          int32_t* d_idx, int32_t* d_perm, void* d_temp, size_t temp_bytes, float minx, float miny, int cells_x,
-                         int key_bits, cudaStream_t s);
+                         int key_bits, int4* d_hyp, cudaStream_t s);
 
 void launch_search(const MapView& map, const SlopeTableDev& table, const TemplatesView& tv, const SceneView& sv,
                    const SearchLaunch& sl, const SearchOutputs& out, cudaStream_t s);

@@ -324,10 +324,11 @@ __device__ __forceinline__ HypDecode decode_hypothesis(long long h, const Templa
 // are written at the hypothesis index.
 __global__ void search_key_kernel(const __grid_constant__ TemplatesView tv, const __grid_constant__ SceneView sv,
                                   const __grid_constant__ SearchLaunch sl, float minx, float miny, int cells_x,
-                                  uint32_t* __restrict__ keys, int32_t* __restrict__ idx) {
+                                  uint32_t* __restrict__ keys, int32_t* __restrict__ idx, int4* __restrict__ hyp) {
     const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= sl.n_hyp) return;
     const HypDecode d = decode_hypothesis(h, tv, sv, sl);
+    hyp[h] = make_int4(d.t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);   // the search kernel reads it back
     const float4 s = sv.lines[d.sline];
     const int cx = min(max((int)(((s.x + s.z) * 0.5f - minx) * (1.f / 128.f)), 0), cells_x - 1);
     const int cy = min(max((int)(((s.y + s.w) * 0.5f - miny) * (1.f / 128.f)), 0), 4095);
@@ -344,8 +345,8 @@ size_t search_order_temp_bytes(int64_t n_hyp) {
 
 void launch_search_order(const TemplatesView& tv, const SceneView& sv, const SearchLaunch& sl, uint32_t* d_keys, uint32_t* d_keys_out,
                          int32_t* d_idx, int32_t* d_perm, void* d_temp, size_t temp_bytes, float minx, float miny, int cells_x,
-                         int key_bits, cudaStream_t s) {
-    search_key_kernel<<<(unsigned)((sl.n_hyp + 255) / 256), 256, 0, s>>>(tv, sv, sl, minx, miny, cells_x, d_keys, d_idx);
+                         int key_bits, int4* d_hyp, cudaStream_t s) {
+    search_key_kernel<<<(unsigned)((sl.n_hyp + 255) / 256), 256, 0, s>>>(tv, sv, sl, minx, miny, cells_x, d_keys, d_idx, d_hyp);
     cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_out, d_idx, d_perm, (int)sl.n_hyp, 0, key_bits, s);
 }
 
@@ -599,9 +600,17 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
         avx = sl.direct_align[h].x;
         avy = sl.direct_align[h].y;
     } else {
-        const HypDecode d = decode_hypothesis(h, tv, sv, sl);
+        HypDecode d;
+        if (sl.hyp_ready) {                   // decoded by the ordering pass
+            const int4 q = sl.hyp_ready[h];
+            d.t = q.x - sl.tmpl_idx_base; d.tline = q.y; d.sline = q.z; d.rev = q.w;
+            d.l0 = tv.offsets[d.t];
+            d.L = tv.offsets[d.t + 1] - d.l0;
+        } else {
+            d = decode_hypothesis(h, tv, sv, sl);
+            if (lane == 0) out.hyp[h] = make_int4(d.t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);
+        }
         t = d.t; l0 = d.l0; L = d.L;
-        if (lane == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);
         T = align_dev(tv.lines[l0 + d.tline], sv.lines[d.sline], d.rev, avx, avy);   // defaultmatch.cpp:57-69
     }
     const float4* TL = tv.lines + l0;
