@@ -17,6 +17,8 @@
 // branches), the top of the stack in registers, the next 32 entries in a shared-memory ring, older ones spilled to a
 // per-row global array.  The pixel fill walks the envelope once per row and goes through a 32x32 shared-memory
 // transposition so that global stores are 128-byte row segments.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -28,8 +30,10 @@ constexpr uint32_t kNone16 = 0xFFFFu;
 // per (plane, band, column): {edge bits of the 32 rows, (rows from the band's first row up to the last edge above) |
 // (rows from the band's last row down to the first edge below) << 16}; 0xFFFF = no such edge
 // =============================================================================================
+// row_range (optional): per plane {-(first row holding an edge), last row holding an edge}, both by atomicMax on a buffer
+// preset to a very negative value
 __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __restrict__ mask, MapDims dm,
-                                                          uint2* __restrict__ info, int nbands) {
+                                                          uint2* __restrict__ info, int nbands, int32_t* __restrict__ row_range) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* M = reinterpret_cast<uint32_t*>(smem_raw);                       // [nbands][64] column bit words
     uint16_t* up16 = reinterpret_cast<uint16_t*>(M + (size_t)nbands * 64);     // [nbands][64]
@@ -62,11 +66,21 @@ __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __rest
     if (threadIdx.x < 64) {
         const int c = threadIdx.x;
         const int x = blockIdx.x * 64 + c;
-        int last = -1;
+        int last = -1, first = 0x7FFFFFF0;
         for (int b = 0; b < nbands; ++b) {
             up16[(size_t)b * 64 + c] = (uint16_t)(last < 0 ? kNone16 : (uint32_t)(b * 32 - last));
             const uint32_t m = M[(size_t)b * 64 + c];
-            if (m) last = b * 32 + 31 - __clz(m);
+            if (m) {
+                if (last < 0) first = b * 32 + __ffs(m) - 1;
+                last = b * 32 + 31 - __clz(m);
+            }
+        }
+        if (row_range) {
+            const int nf = __reduce_max_sync(0xffffffffu, -first), nl = __reduce_max_sync(0xffffffffu, last);
+            if ((threadIdx.x & 31) == 0 && nl >= 0) {
+                atomicMax(row_range + 2 * d, nf);
+                atomicMax(row_range + 2 * d + 1, nl);
+            }
         }
         int next = -1;
         uint2* out = info + (size_t)d * nbands * dm.pitch + x;
@@ -157,11 +171,14 @@ struct RowStack {
     }
     // first pixel from which parabola (v, key), v right of every vertex of the stack, beats the envelope (imgproc.h:
     // 104-120 on integers; the left parabola keeps ties); pops the vertices that end up owning nothing; >= W: never
+    // kLoose (candidate pass, see dt_row_band_kernel): the top is only popped when the new parabola takes over at least one
+    // pixel BEFORE the top's first one; a vertex popped that way is nowhere strictly minimal, even between pixels
+    template <bool kLoose = false>
     __device__ __forceinline__ int take_over(int v, uint32_t key, int Wm1) {
         while (k >= 0) {
             const int N = (int)key - (int)topkey;
             const int Dn = 2 * (v - topv);
-            if (N < tops * Dn) {                 // from a pixel not after the top's first one: the top owns nothing
+            if (N < (tops - (kLoose ? 1 : 0)) * Dn) {   // from a pixel not after the top's first one: the top owns nothing
                 pop();
                 continue;
             }
@@ -171,20 +188,22 @@ struct RowStack {
         return 0;
     }
     // left stack, one column: ascending v
+    template <bool kLoose = false>
     __device__ __forceinline__ void column(int v, int gv, int Wm1) {
         const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
-        const int start = take_over(v, key, Wm1);
+        const int start = take_over<kLoose>(v, key, Wm1);
         if (start <= Wm1) push(v, start, key);
     }
     // right stack, one column: descending v.  Parabola v (left of every vertex of the stack) is not worse than the top up
     // to pixel floor(N / Dn) (it keeps ties); the top is popped when that reaches the top's last pixel.
+    template <bool kLoose = false>
     __device__ __forceinline__ void column_rev(int v, int gv, int Wm1) {
         const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
         int end = Wm1;
         while (k >= 0) {
             const int N = (int)topkey - (int)key;
             const int Dn = 2 * (topv - v);
-            if (N >= tops * Dn) {
+            if (N >= (tops + (kLoose ? 1 : 0)) * Dn) {
                 pop();
                 continue;
             }
@@ -220,21 +239,27 @@ struct RowMeta {
 // chain per row is half as long as with one stack and twice as many warps are in flight.
 // Workspace rows are padded to 32 per band (row id = (d * nbands + b) * 32 + lane) so that the rows past H of the last
 // band need no special case: they build an envelope nobody reads.
-template <bool kFromG, bool kRev>
+// kCand: candidate pass for one row (row `rsel` of the band, lane 0 only, loose pops).  cand: 1 bit per column, columns
+// whose bit is clear are skipped (far bands).
+template <bool kFromG, bool kRev, bool kCand>
 __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restrict__ info_row, const uint16_t* __restrict__ g,
                                               const uint16_t* __restrict__ g_row, const MapDims& dm, int d, int row0, int x_begin,
-                                              int x_end, int lane) {
+                                              int x_end, int lane, int rsel, const uint32_t* __restrict__ cand) {
     const int W = dm.W, Wm1 = dm.W - 1;
-    const uint32_t mle = 0xFFFFFFFFu >> (31 - lane), mge = 0xFFFFFFFFu << lane;
-    const int l31 = 31 - lane;
+    const uint32_t mle = 0xFFFFFFFFu >> (31 - rsel), mge = 0xFFFFFFFFu << rsel;
+    const int l31 = 31 - rsel;
     const uint2 kNone = make_uint2(0u, 0xFFFFFFFFu);
     const int nchunks = (x_end - x_begin) >> 5;
     auto chunk_x0 = [&](int c) { return kRev ? x_end - 32 * (c + 1) : x_begin + 32 * c; };
     uint2 e_next = kNone;
     if (!kFromG && nchunks > 0 && chunk_x0(0) + lane < W) e_next = info_row[chunk_x0(0)];
+    uint32_t cw_next = 0xFFFFFFFFu;
+    if (cand && nchunks > 0) cw_next = __ldcg(cand + (chunk_x0(0) >> 5));
     for (int c = 0; c < nchunks; ++c) {
         const int x0 = chunk_x0(c);
         const uint2 e = e_next;
+        const uint32_t cw = cw_next;
+        if (cand && c + 1 < nchunks) cw_next = __ldcg(cand + (chunk_x0(c + 1) >> 5));
         unsigned todo;
         if (kFromG) {
             // lane = column here: which of the 32 columns hold a finite value in ANY row of the band
@@ -245,7 +270,7 @@ __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restr
         } else {
             e_next = kNone;
             if (c + 1 < nchunks && chunk_x0(c + 1) + lane < W) e_next = info_row[chunk_x0(c + 1)];   // one iteration ahead
-            todo = __ballot_sync(0xffffffffu, e.x != 0u || e.y != 0xFFFFFFFFu);
+            todo = __ballot_sync(0xffffffffu, e.x != 0u || e.y != 0xFFFFFFFFu) & cw;
         }
         const bool no_bits = kFromG || __ballot_sync(0xffffffffu, e.x != 0u) == 0u;   // no edge pixel inside the band here
         while (todo) {
@@ -259,47 +284,120 @@ __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restr
             } else if (no_bits) {
                 // g = distance to the nearest edge above / below the band
                 const uint32_t ud = __shfl_sync(0xffffffffu, e.y, j);
-                gv = min(lane + (int)(ud & 0xFFFFu), l31 + (int)(ud >> 16));
+                gv = min(rsel + (int)(ud & 0xFFFFu), l31 + (int)(ud >> 16));
             } else {
                 const uint32_t M = __shfl_sync(0xffffffffu, e.x, j), ud = __shfl_sync(0xffffffffu, e.y, j);
                 const uint32_t above = M & mle, below = M & mge;
                 const int ua = __clz(above) - 31, ub = (int)(ud & 0xFFFFu);       // lane - (row of the last edge at or above)
                 const int da = __ffs(below) - 1 - 31, db = (int)(ud >> 16);       // (row of the first edge at or below) - 31
-                gv = min(lane + (above ? ua : ub), l31 + (below ? da : db));
+                gv = min(rsel + (above ? ua : ub), l31 + (below ? da : db));
             }
+            if (kCand) fin = lane == 0;
             if (fin) {
-                if (kRev) st.column_rev(x0 + j, gv, Wm1);
-                else st.column(x0 + j, gv, Wm1);
+                if (kRev) st.template column_rev<kCand>(x0 + j, gv, Wm1);
+                else st.template column<kCand>(x0 + j, gv, Wm1);
             }
         }
     }
 }
 
+// Candidate pruning for far bands.  Let r_top / r_bot be the first / last row of a plane that holds an edge pixel.  For a
+// row y above r_top every site is the top-most edge pixel of its column, and if column v owns an (integer) pixel P of row
+// y, then on the whole open segment from P to that site the site is the STRICTLY nearest one; the segment crosses row
+// y0 = r_top - 1, so v has an interval of positive length on the continuous lower envelope of row y0.  Hence the columns
+// that survive a stack pass over row y0 which only pops vertices that are nowhere strictly minimal (kLoose) are a
+// superset of the owners of every row above; the same holds below r_bot with y0 = r_bot + 1.  The first 2*D CTAs of the
+// grid run that pass (one (plane, side) each, left / right halves by the two warps, lane 0 only) and publish a
+// column bit mask; bands that lie entirely above r_top or below r_bot wait for it and skip all other columns.
+struct BandAux {
+    int32_t* row_range;     // [D][2]  {-(first edge row), last edge row}; very negative when the plane has no edge
+    int32_t* flags;         // [D][2]  set when the candidate mask of (plane, side) is complete
+    uint32_t* cand;         // [D][2][wwords]
+};
+
 template <bool kFromG>
 __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict__ info, const uint16_t* __restrict__ g, MapDims dm,
                                                          int nbands, uint2* __restrict__ spill_all, int maxdepth,
-                                                         RowMeta* __restrict__ row_meta, int xsplit) {
+                                                         RowMeta* __restrict__ row_meta, int xsplit, BandAux aux, int n_cand_ctas) {
     __shared__ __align__(16) uint2 ring_all[2][kRing * 32];
     __shared__ int s_kright[32];
+    __shared__ int s_kleft;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wg = blockIdx.x;                              // band id, plane-fastest (neighbouring CTAs: different planes)
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring_all[warp]) + (uint32_t)lane * 8u;
+    const int Wm1 = dm.W - 1;
+
+    if ((int)blockIdx.x < n_cand_ctas) {
+        // ---- candidate pass of one (plane, side) ----
+        const int d = blockIdx.x >> 1, side = blockIdx.x & 1;
+        const int r_top = -aux.row_range[2 * d], r_bot = aux.row_range[2 * d + 1];
+        const int y0 = side == 0 ? r_top - 1 : r_bot + 1;
+        if (r_bot < 0 || y0 < 0 || y0 >= dm.H) {           // no edge in the plane, or no row on that side
+            if (threadIdx.x == 0) atomicExch(aux.flags + blockIdx.x, 1);
+            return;
+        }
+        const uint2* info_row = info + ((size_t)d * nbands + (y0 >> 5)) * dm.pitch + lane;
+        uint2* row_entries = spill_all + ((size_t)dm.D * nbands * 32 + blockIdx.x) * maxdepth;   // rows after the padded planes
+        RowStack st;
+        int kmine;
+        if (warp == 1) {
+            st.init(ring_addr, row_entries + (maxdepth - 1), -1);
+            envelope_half<false, true, true>(st, info_row, nullptr, nullptr, dm, d, y0 & ~31, xsplit, dm.pitch, lane, y0 & 31, nullptr);
+            kmine = st.park();
+            if (lane == 0) s_kright[0] = kmine;
+        } else {
+            st.init(ring_addr, row_entries, 1);
+            envelope_half<false, false, true>(st, info_row, nullptr, nullptr, dm, d, y0 & ~31, 0, xsplit, lane, y0 & 31, nullptr);
+            kmine = st.park();
+            if (lane == 0) s_kleft = kmine;
+        }
+        __syncthreads();
+        uint32_t* cw = aux.cand + (size_t)blockIdx.x * dm.wwords;
+        const int kl = s_kleft, kr = s_kright[0];
+        for (int i = threadIdx.x; i < kl + kr; i += blockDim.x) {
+            const uint2 e = i < kl ? row_entries[i] : row_entries[maxdepth - kr + (i - kl)];
+            const int v = (int)(e.y & 0xFFFFu);
+            atomicOr(cw + (v >> 5), 1u << (v & 31));
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicExch(aux.flags + blockIdx.x, 1);
+        return;
+    }
+
+    const int wg = blockIdx.x - n_cand_ctas;                // band id, plane-fastest (neighbouring CTAs: different planes)
     const int d = wg % dm.D, b = wg / dm.D;
     const int row0 = b * 32;
-    const int Wm1 = dm.W - 1;
     const uint2* info_row = info + ((size_t)d * nbands + b) * dm.pitch + lane;
     const uint16_t* g_row = kFromG ? g + ((size_t)d * dm.H + min(row0 + lane, dm.H - 1)) * dm.pitch : nullptr;
     const size_t prow = ((size_t)d * nbands + b) * 32 + lane;
     uint2* row_entries = spill_all + prow * maxdepth;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring_all[warp]) + (uint32_t)lane * 8u;
+
+    const uint32_t* cand = nullptr;
+    if (n_cand_ctas > 0) {
+        const int r_top = -aux.row_range[2 * d], r_bot = aux.row_range[2 * d + 1];
+        int side = -1;
+        if (r_bot >= 0) {
+            if (row0 + 31 < r_top) side = 0;                // the whole band lies above the first edge row
+            else if (row0 > r_bot) side = 1;                // ... below the last one
+        }
+        if (side >= 0) {
+            if (lane == 0) {
+                volatile int32_t* f = aux.flags + 2 * d + side;
+                while (*f == 0) __nanosleep(256);
+            }
+            __syncwarp();
+            cand = aux.cand + (size_t)(2 * d + side) * dm.wwords;
+        }
+    }
 
     RowStack st;
     if (warp == 1) {
         st.init(ring_addr, row_entries + (maxdepth - 1), -1);
-        envelope_half<kFromG, true>(st, info_row, g, g_row, dm, d, row0, xsplit, dm.pitch, lane);
+        envelope_half<kFromG, true, false>(st, info_row, g, g_row, dm, d, row0, xsplit, dm.pitch, lane, lane, cand);
         s_kright[lane] = st.park();
     } else {
         st.init(ring_addr, row_entries, 1);
-        envelope_half<kFromG, false>(st, info_row, g, g_row, dm, d, row0, 0, xsplit, lane);
+        envelope_half<kFromG, false, false>(st, info_row, g, g_row, dm, d, row0, 0, xsplit, lane, lane, cand);
     }
     __syncthreads();
     if (warp != 0) return;
@@ -747,13 +845,34 @@ static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1
 int dt_band_count(const MapDims& dm) { return (dm.H + 31) / 32; }
 size_t dt_band_info_bytes(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * dm.pitch * sizeof(uint2); }
 static size_t padded_rows(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * 32; }
+static size_t aux_ints(const MapDims& dm) { return (size_t)dm.D * 4 + (size_t)dm.D * 2 * dm.wwords; }   // row range, flags, masks
 static size_t row_k_bytes(const MapDims& dm) { return (padded_rows(dm) * sizeof(RowMeta) + 255) / 256 * 256; }
 // workspace of the row call: per-row RowMeta + per-row envelope array of maxdepth entries
 size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth) {
-    return row_k_bytes(dm) + padded_rows(dm) * (size_t)maxdepth * sizeof(uint2);
+    return row_k_bytes(dm) + (padded_rows(dm) + 2 * (size_t)dm.D) * (size_t)maxdepth * sizeof(uint2) + aux_ints(dm) * 4;
 }
 
-void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, cudaStream_t s) {
+static BandAux band_aux(const MapDims& dm, void* d_ws, int maxdepth) {
+    unsigned char* p = reinterpret_cast<unsigned char*>(d_ws) + row_k_bytes(dm) +
+                       (padded_rows(dm) + 2 * (size_t)dm.D) * (size_t)maxdepth * sizeof(uint2);
+    BandAux a;
+    a.row_range = reinterpret_cast<int32_t*>(p);
+    a.flags = a.row_range + 2 * dm.D;
+    a.cand = reinterpret_cast<uint32_t*>(a.flags + 2 * dm.D);
+    return a;
+}
+
+// d_ws / maxdepth: the row-call workspace when the plane row ranges are wanted (candidate pruning), else nullptr
+void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
+    int32_t* row_range = nullptr;
+    if (d_ws) {
+        int lo = win_lo < 0 ? 0 : win_lo, hi = win_hi >= dm.W ? dm.W - 1 : win_hi;
+        if (hi < lo) { lo = 0; hi = dm.W - 1; }
+        const BandAux a = band_aux(dm, d_ws, hi - lo + 1);
+        cudaMemsetAsync(a.row_range, 0x80, (size_t)dm.D * 2 * 4, s);                                 // very negative
+        cudaMemsetAsync(a.flags, 0, ((size_t)dm.D * 2 + (size_t)dm.D * 2 * dm.wwords) * 4, s);       // flags + masks
+        row_range = a.row_range;
+    }
     const int nbands = dt_band_count(dm);
     const size_t smem = (size_t)nbands * 64 * 6;
     dim3 grid((dm.wwords + 1) / 2, dm.D);
@@ -762,7 +881,7 @@ void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info,
         cudaFuncSetAttribute(dt_col_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_smem = smem;
     }
-    dt_col_band_kernel<<<grid, 256, smem, s>>>(d_mask, dm, reinterpret_cast<uint2*>(d_info), nbands);
+    dt_col_band_kernel<<<grid, 256, smem, s>>>(d_mask, dm, reinterpret_cast<uint2*>(d_info), nbands, row_range);
 }
 
 // [win_lo, win_hi]: columns that can hold an edge pixel (envelope vertices only exist there)
@@ -779,14 +898,18 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
                             cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int nbands = dt_band_count(dm);
-    const unsigned grid = (unsigned)(dm.D * nbands);
     // split column: middle of the window that can hold edge pixels, on a 32-column boundary
     const int xsplit = min(dm.pitch, max(0, ((ws.win_lo + ws.win_lo + ws.maxdepth) / 2) & ~31));
-    if (d_g)
-        dt_row_band_kernel<true><<<grid, 64, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit);
-    else
-        dt_row_band_kernel<false><<<grid, 64, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands, ws.spill, ws.maxdepth,
-                                                     ws.row_k, xsplit);
+    static const bool no_prune = [] { const char* e = getenv("FDCM_NO_PRUNE"); return e && e[0] == '1'; }();
+    if (d_g) {
+        dt_row_band_kernel<true><<<(unsigned)(dm.D * nbands), 64, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
+                                                                          BandAux{nullptr, nullptr, nullptr}, 0);
+    } else {
+        const int n_cand = no_prune ? 0 : 2 * dm.D;
+        dt_row_band_kernel<false><<<(unsigned)(dm.D * nbands + n_cand), 64, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
+                                                                                    ws.spill, ws.maxdepth, ws.row_k, xsplit,
+                                                                                    band_aux(dm, d_ws, ws.maxdepth), n_cand);
+    }
 }
 
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
