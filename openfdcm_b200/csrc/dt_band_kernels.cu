@@ -318,7 +318,8 @@ struct BandAux {
 template <bool kFromG>
 __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict__ info, const uint16_t* __restrict__ g, MapDims dm,
                                                          int nbands, uint2* __restrict__ spill_all, int maxdepth,
-                                                         RowMeta* __restrict__ row_meta, int xsplit, BandAux aux, int n_cand_ctas) {
+                                                         RowMeta* __restrict__ row_meta, int xsplit, BandAux aux, int n_cand_ctas, int band_lo,
+                                                         int band_hi) {
     __shared__ __align__(16) uint2 ring_all[2][kRing * 32];
     __shared__ int s_kright[32];
     __shared__ int s_kleft;
@@ -364,8 +365,15 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
         return;
     }
 
-    const int wg = blockIdx.x - n_cand_ctas;                // band id, plane-fastest (neighbouring CTAs: different planes)
-    const int d = wg % dm.D, b = wg / dm.D;
+    // plane-fastest (neighbouring CTAs: different planes); the bands that overlap the scene's rows come first in the grid:
+    // they carry the long serial chains, the others mostly wait for their candidate mask
+    const int wg = blockIdx.x - n_cand_ctas;
+    const int d = wg % dm.D;
+    int b = wg / dm.D;
+    {
+        const int n_in = band_hi - band_lo + 1;
+        b = b < n_in ? band_lo + b : (b - n_in < band_lo ? b - n_in : b);
+    }
     const int row0 = b * 32;
     const uint2* info_row = info + ((size_t)d * nbands + b) * dm.pitch + lane;
     const uint16_t* g_row = kFromG ? g + ((size_t)d * dm.H + min(row0 + lane, dm.H - 1)) * dm.pitch : nullptr;
@@ -380,12 +388,12 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
             if (row0 + 31 < r_top) side = 0;                // the whole band lies above the first edge row
             else if (row0 > r_bot) side = 1;                // ... below the last one
         }
-        if (side >= 0) {
-            if (lane == 0) {
-                volatile int32_t* f = aux.flags + 2 * d + side;
-                while (*f == 0) __nanosleep(256);
+        if (side >= 0) {                                    // (uniform over the CTA)
+            if (threadIdx.x == 0) {                         // one polling thread per CTA, long naps: the spin must not eat
+                volatile int32_t* f = aux.flags + 2 * d + side;   // the issue slots of the bands that do real work
+                while (*f == 0) __nanosleep(2000);
             }
-            __syncwarp();
+            __syncthreads();
             cand = aux.cand + (size_t)(2 * d + side) * dm.wwords;
         }
     }
@@ -895,20 +903,22 @@ static RowWs row_ws(const MapDims& dm, void* d_ws, int win_lo, int win_hi) {
 }
 
 void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi,
-                            cudaStream_t s) {
+                            int row_lo, int row_hi, cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int nbands = dt_band_count(dm);
     // split column: middle of the window that can hold edge pixels, on a 32-column boundary
     const int xsplit = min(dm.pitch, max(0, ((ws.win_lo + ws.win_lo + ws.maxdepth) / 2) & ~31));
     static const bool no_prune = [] { const char* e = getenv("FDCM_NO_PRUNE"); return e && e[0] == '1'; }();
+    int band_lo = (row_lo < 0 ? 0 : row_lo) >> 5, band_hi = (row_hi >= dm.H ? dm.H - 1 : row_hi) >> 5;
+    if (band_hi < band_lo || band_hi >= nbands) { band_lo = 0; band_hi = nbands - 1; }
     if (d_g) {
         dt_row_band_kernel<true><<<(unsigned)(dm.D * nbands), 64, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
-                                                                          BandAux{nullptr, nullptr, nullptr}, 0);
+                                                                          BandAux{nullptr, nullptr, nullptr}, 0, band_lo, band_hi);
     } else {
         const int n_cand = no_prune ? 0 : 2 * dm.D;
         dt_row_band_kernel<false><<<(unsigned)(dm.D * nbands + n_cand), 64, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
                                                                                     ws.spill, ws.maxdepth, ws.row_k, xsplit,
-                                                                                    band_aux(dm, d_ws, ws.maxdepth), n_cand);
+                                                                                    band_aux(dm, d_ws, ws.maxdepth), n_cand, band_lo, band_hi);
     }
 }
 

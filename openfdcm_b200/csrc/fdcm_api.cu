@@ -208,6 +208,7 @@ struct fdcm_dt3 {
     float shift[2] = {0.f, 0.f};
     bool exact = true;
     int col_lo = 0, col_hi = 0;  // column range that can hold edge pixels (bbox of the shifted scene)
+    int row_lo = 0, row_hi = 0;  // row range likewise
     bool row_literal = false;   // FDCM_ROW_LITERAL=1: use the literal row pass even in the exact regime (A/B testing)
     int n_lines = 0;
     std::vector<float> keys;
@@ -360,10 +361,17 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     {
         // clipping only moves end points inwards and pixels are round()ed coordinates: every edge pixel column lies in
         // [floor(min x), ceil(max x)] of the shifted scene
-        float mnx = ts[0], mxx = ts[0];
+        float mnx = ts[0], mxx = ts[0], mny = ts[1], mxy = ts[1];
         for (int64_t i = 0; i < 2 * (int64_t)n_lines; ++i) {
             mnx = std::min(mnx, ts[2 * i]);
             mxx = std::max(mxx, ts[2 * i]);
+            mny = std::min(mny, ts[2 * i + 1]);
+            mxy = std::max(mxy, ts[2 * i + 1]);
+        }
+        {
+            const double lo = std::floor((double)mny) - 1.0, hi = std::ceil((double)mxy) + 1.0;
+            m->row_lo = (lo < 0.0 || !(lo == lo)) ? 0 : (lo > dm.H - 1 ? dm.H - 1 : (int)lo);
+            m->row_hi = (!(hi == hi) || hi > dm.H - 1) ? dm.H - 1 : (hi < 0.0 ? 0 : (int)hi);
         }
         const double lo = std::floor((double)mnx) - 1.0, hi = std::ceil((double)mxx) + 1.0;
         m->col_lo = (lo < 0.0 || !(lo == lo)) ? 0 : (lo > dm.W - 1 ? dm.W - 1 : (int)lo);
@@ -452,7 +460,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
         }
         {
             KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
-            launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+            launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, s);
         }
         fused_propagate = m->stage != 1 && m->fuse_fill && dt_fill_propagate_supported(dm);
         if (fused_propagate) {
@@ -1341,7 +1349,7 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
     if (e == cudaSuccess) {
         KernelScope k(literal == 2 ? "dt_row_band" : (literal ? "dt_row_literal" : "dt_row_exact"), 0.0, s);
         if (literal == 2) {
-            launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, s);
+            launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, 0, dm.H - 1, s);
             launch_dt_row_fill(dp.as<float>(), dm, ds.p, 0, dm.W - 1, s);
         }
         else if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);

@@ -24,7 +24,9 @@ size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth);
 // d_ws (row-call workspace, may be null): also records every plane's first / last edge row there (candidate pruning)
 void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
 // d_info (band records) or d_g (explicit u16 rows, tests) feeds the envelope build; exactly one of them is non-null
-void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
+// [row_lo, row_hi]: rows that can hold edge pixels (only used to order the bands in the grid)
+void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi, int row_lo,
+                            int row_hi, cudaStream_t s);
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
 // fill fused with propagateOrientation (and the L2 sqrt): the distance-transform planes never reach HBM
 bool dt_fill_propagate_supported(const MapDims& dm);
