@@ -873,7 +873,7 @@ __global__ void __launch_bounds__(1024) topk_level2_kernel(const fdcm_match* __r
 }
 
 int topk_ws_blocks(int64_t n) {
-    const int64_t per_block = 1024 * 16;
+    const int64_t per_block = 1024 * 2;
     int64_t b = (n + per_block - 1) / per_block;
     if (b < 1) b = 1;
     if (b > 592) b = 592;   // 4 x 148 SMs
