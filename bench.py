@@ -184,7 +184,7 @@ def main():
         return fd.allgather_topk(top, TOP_K, device=dev) if world > 1 else top
 
     def step_resident():
-        fm.rerun()
+        fm.rerun(wait=False)   # queued; the search below is stream-ordered after it and ends with the only host sync of the step
         return merge(fdcm.search_topk(fm, tset, None, searcher, optimizer, penalty, TOP_K, base))
 
     def step_e2e():

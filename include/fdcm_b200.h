@@ -117,6 +117,8 @@ fdcm_status fdcm_dt3_rebuild(fdcm_dt3* map, const float* scene_xyxy, int32_t n_l
 fdcm_status fdcm_dt3_rebuild_async(fdcm_dt3* map, const float* scene_xyxy, int32_t n_lines);
 /* Re-run the build kernels on the scene lines already resident on the device (kernel-only timing). */
 fdcm_status fdcm_dt3_rerun(fdcm_dt3* map);
+/* fdcm_dt3_rerun without the final wait (stream-ordered before any later call on this map). */
+fdcm_status fdcm_dt3_rerun_async(fdcm_dt3* map);
 fdcm_status fdcm_dt3_retain(fdcm_dt3* map);
 fdcm_status fdcm_dt3_release(fdcm_dt3* map);
 fdcm_status fdcm_dt3_get_info(const fdcm_dt3* map, fdcm_dt3_info* info);

@@ -140,8 +140,8 @@ class Dt3Cuda:
         check((lib().fdcm_dt3_rebuild if wait else lib().fdcm_dt3_rebuild_async)(self._h, ptr(r), r.shape[0]))
         self._refresh()
 
-    def rerun(self):
-        check(lib().fdcm_dt3_rerun(self._h))
+    def rerun(self, wait=True):
+        check((lib().fdcm_dt3_rerun if wait else lib().fdcm_dt3_rerun_async)(self._h))
 
     def last_search_stats(self):
         st = _lib.SearchStats()

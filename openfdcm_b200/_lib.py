@@ -48,6 +48,7 @@ SIGNATURES = {
     "fdcm_dt3_rebuild": (C.c_int, [_P, _P, C.c_int32]),
     "fdcm_dt3_rebuild_async": (C.c_int, [_P, _P, C.c_int32]),
     "fdcm_dt3_rerun": (C.c_int, [_P]),
+    "fdcm_dt3_rerun_async": (C.c_int, [_P]),
     "fdcm_dt3_retain": (C.c_int, [_P]),
     "fdcm_dt3_release": (C.c_int, [_P]),
     "fdcm_dt3_get_info": (C.c_int, [_P, C.POINTER(Dt3Info)]),

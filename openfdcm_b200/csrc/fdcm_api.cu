@@ -606,6 +606,14 @@ extern "C" fdcm_status fdcm_dt3_rerun(fdcm_dt3* m) {
     return st;
 }
 
+extern "C" fdcm_status fdcm_dt3_rerun_async(fdcm_dt3* m) {
+    if (!m) return fail(FDCM_ERR_INVALID, "map is null");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    return run_build_kernels(m, s);
+}
+
 extern "C" fdcm_status fdcm_dt3_retain(fdcm_dt3* m) {
     if (!m) return fail(FDCM_ERR_INVALID, "map is null");
     m->refs.fetch_add(1);
