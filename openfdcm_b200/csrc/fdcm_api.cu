@@ -784,9 +784,21 @@ struct fdcm_templates {
     // uploads run on the copy stream (they overlap a map build in flight on the main stream); consumers wait on `ready`
     cudaEvent_t ready = nullptr;
     bool upload_pending = false;
+    void* h_stage = nullptr;          // pinned staging for the small per-search uploads (denominators, hypothesis offsets)
+    size_t h_stage_cap = 0;
+    cudaError_t stage_reserve(size_t bytes) {
+        if (bytes <= h_stage_cap) return cudaSuccess;
+        if (h_stage) cudaFreeHost(h_stage);
+        h_stage = nullptr;
+        h_stage_cap = 0;
+        cudaError_t e = cudaMallocHost(&h_stage, bytes);
+        if (e == cudaSuccess) h_stage_cap = bytes;
+        return e;
+    }
     ~fdcm_templates() {
         cudaSetDevice(device);
         if (ready) cudaEventDestroy(ready);
+        if (h_stage) cudaFreeHost(h_stage);
         for (DevBuf* b : {&lines, &offs, &argsort, &line_len, &denom}) b->release();
     }
 };
@@ -1041,28 +1053,41 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     m->last_stats.n_hypotheses = H;
     if (H == 0) return FDCM_OK;
 
-    // penalty denominators (host powf, like the reference) cached per (kind, tau)
-    const float* d_denom = nullptr;
-    if (p->penalty_kind != FDCM_PENALTY_NONE) {
-        std::lock_guard<std::mutex> lk2(t->mu);
-        if (t->denom_kind != p->penalty_kind || t->denom_tau != p->penalty_tau) {
-            std::vector<float> den((size_t)t->n_tmpl);
-            for (int i = 0; i < t->n_tmpl; ++i) den[(size_t)i] = penalty_denominator(p->penalty_kind, p->penalty_tau, t->lengths[(size_t)i]);
-            CUDA_TRY(cudaMemcpyAsync(t->denom.p, den.data(), den.size() * 4, cudaMemcpyHostToDevice, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-            t->denom_kind = p->penalty_kind;
-            t->denom_tau = p->penalty_tau;
-        }
-        d_denom = t->denom.as<float>();
-    }
-
     // ---- workspace ----
     CUDA_TRY(m->s_hyp_off.reserve(hyp_off.size() * 8));
     CUDA_TRY(m->s_rec.reserve((size_t)H * sizeof(fdcm_match)));
     CUDA_TRY(m->s_valid.reserve((size_t)H));
     CUDA_TRY(m->s_hyp.reserve((size_t)H * 16));
     CUDA_TRY(m->s_counters.reserve(3 * 8));
-    CUDA_TRY(cudaMemcpyAsync(m->s_hyp_off.p, hyp_off.data(), hyp_off.size() * 8, cudaMemcpyHostToDevice, s));
+
+    // Small per-search uploads (penalty denominators: host powf like the reference, cached per (kind, tau); hypothesis
+    // offsets) go through pinned staging on the copy stream: a pageable copy on the main stream would first wait for
+    // everything queued there, e.g. a map build in flight.
+    const float* d_denom = nullptr;
+    {
+        std::lock_guard<std::mutex> lk2(t->mu);
+        cudaStream_t cs;
+        if (fdcm_status st = get_copy_stream(m->device, &cs)) return st;
+        if (!t->ready) CUDA_TRY(cudaEventCreateWithFlags(&t->ready, cudaEventDisableTiming));
+        else CUDA_TRY(cudaEventSynchronize(t->ready));   // the staging buffer may still feed an earlier upload (other threads)
+        const size_t off_bytes = hyp_off.size() * 8, den_bytes = (size_t)t->n_tmpl * 4;
+        CUDA_TRY(t->stage_reserve(off_bytes + den_bytes));
+        std::memcpy(t->h_stage, hyp_off.data(), off_bytes);
+        CUDA_TRY(cudaMemcpyAsync(m->s_hyp_off.p, t->h_stage, off_bytes, cudaMemcpyHostToDevice, cs));
+        if (p->penalty_kind != FDCM_PENALTY_NONE) {
+            if (t->denom_kind != p->penalty_kind || t->denom_tau != p->penalty_tau) {
+                float* den = reinterpret_cast<float*>(static_cast<unsigned char*>(t->h_stage) + off_bytes);
+                for (int i = 0; i < t->n_tmpl; ++i) den[i] = penalty_denominator(p->penalty_kind, p->penalty_tau, t->lengths[(size_t)i]);
+                CUDA_TRY(cudaMemcpyAsync(t->denom.p, den, den_bytes, cudaMemcpyHostToDevice, cs));
+                t->denom_kind = p->penalty_kind;
+                t->denom_tau = p->penalty_tau;
+            }
+            d_denom = t->denom.as<float>();
+        }
+        CUDA_TRY(cudaEventRecord(t->ready, cs));
+        CUDA_TRY(cudaStreamWaitEvent(s, t->ready, 0));
+        t->upload_pending = false;   // (this event is recorded after any template upload on the same copy stream)
+    }
     CUDA_TRY(cudaMemsetAsync(m->s_counters.p, 0, 3 * 8, s));
 
     TemplatesView tv;
