@@ -236,6 +236,9 @@ struct fdcm_dt3 {
     std::vector<float> h_build_scene;   // host copy of the build scene (for scene == NULL searches with a new filter)
     mutable int64_t last_n_hyp = 0;
     mutable fdcm_search_stats last_stats{};
+    mutable void* h_scene_stage = nullptr;   // pinned staging for the search-scene upload (truly asynchronous copies)
+    mutable size_t h_scene_stage_cap = 0;
+    mutable cudaEvent_t scene_stage_ev = nullptr;
     mutable void* h_pinned = nullptr;   // pinned staging for match download
     mutable size_t h_pinned_cap = 0;
 
@@ -246,6 +249,8 @@ struct fdcm_dt3 {
                           &s_perm, &s_sort_tmp})
             b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
+        if (h_scene_stage) cudaFreeHost(h_scene_stage);
+        if (scene_stage_ev) cudaEventDestroy(scene_stage_ev);
         destroy_host_tset();
     }
     void destroy_host_tset();
@@ -297,12 +302,28 @@ static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, in
     CUDA_TRY(m->s_scene.reserve((size_t)n_scene * 16));
     CUDA_TRY(m->s_sorted_len.reserve(std::max<size_t>(4, (size_t)ns * 4)));
     CUDA_TRY(m->s_sorted_idx.reserve(std::max<size_t>(4, (size_t)ns * 4)));
-    CUDA_TRY(cudaMemcpyAsync(m->s_scene.p, scene, (size_t)n_scene * 16, cudaMemcpyHostToDevice, s));
-    if (ns) {
-        CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, sorted_len.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, s));
-        CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, sorted_idx.data(), (size_t)ns * 4, cudaMemcpyHostToDevice, s));
+    // through pinned staging: the copies queue behind whatever runs on the stream (e.g. the map build) without making the
+    // host wait for it, which a copy from pageable memory would
+    const size_t need = (size_t)n_scene * 16 + (size_t)ns * 8;
+    if (!m->scene_stage_ev) CUDA_TRY(cudaEventCreateWithFlags(&m->scene_stage_ev, cudaEventDisableTiming));
+    else CUDA_TRY(cudaEventSynchronize(m->scene_stage_ev));   // the staging buffer may still feed the previous upload
+    if (m->h_scene_stage_cap < need) {
+        if (m->h_scene_stage) cudaFreeHost(m->h_scene_stage);
+        m->h_scene_stage = nullptr;
+        m->h_scene_stage_cap = 0;
+        CUDA_TRY(cudaMallocHost(&m->h_scene_stage, need));
+        m->h_scene_stage_cap = need;
     }
-    CUDA_TRY(cudaStreamSynchronize(s));   // pageable temporaries
+    unsigned char* st = static_cast<unsigned char*>(m->h_scene_stage);
+    std::memcpy(st, scene, (size_t)n_scene * 16);
+    CUDA_TRY(cudaMemcpyAsync(m->s_scene.p, st, (size_t)n_scene * 16, cudaMemcpyHostToDevice, s));
+    if (ns) {
+        std::memcpy(st + (size_t)n_scene * 16, sorted_len.data(), (size_t)ns * 4);
+        std::memcpy(st + (size_t)n_scene * 16 + (size_t)ns * 4, sorted_idx.data(), (size_t)ns * 4);
+        CUDA_TRY(cudaMemcpyAsync(m->s_sorted_len.p, st + (size_t)n_scene * 16, (size_t)ns * 4, cudaMemcpyHostToDevice, s));
+        CUDA_TRY(cudaMemcpyAsync(m->s_sorted_idx.p, st + (size_t)n_scene * 16 + (size_t)ns * 4, (size_t)ns * 4, cudaMemcpyHostToDevice, s));
+    }
+    CUDA_TRY(cudaEventRecord(m->scene_stage_ev, s));
     m->s_scene_n = n_scene;
     m->s_sorted_n = ns;
     m->s_filter_on = flt.on;
@@ -417,8 +438,14 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     CUDA_TRY(m->bins.reserve((size_t)n_lines * 4));
     CUDA_TRY(cudaMemcpyAsync(m->lines.p, ts.data(), (size_t)n_lines * 16, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(m->bins.p, m->scene_bins.data(), (size_t)n_lines * 4, cudaMemcpyHostToDevice, s));
-    CUDA_TRY(cudaStreamSynchronize(s));   // ts / scene_bins are pageable temporaries
-    // keep the original scene resident for searches that pass scene == NULL
+    // (copies from pageable memory return once the source has been staged: ts may go out of scope)
+    return FDCM_OK;
+}
+
+// second half of the host preparation, queued AFTER the build kernels so that its host work (length ordering of the
+// scene lines) overlaps the device build: keep the original scene resident for searches that pass scene == NULL
+static fdcm_status upload_build_scene(fdcm_dt3* m, const float* scene, int32_t n_lines, cudaStream_t s) {
+    if (n_lines == 0) return FDCM_OK;
     std::lock_guard<std::mutex> lk(m->search_mutex);
     m->h_build_scene.assign(scene, scene + 4 * (size_t)n_lines);
     m->s_resident_is_build = true;
@@ -552,6 +579,7 @@ extern "C" fdcm_status fdcm_dt3_build(const float* scene_xyxy, int32_t n_lines, 
     m->stage = stage;
     fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
     if (st == FDCM_OK) st = run_build_kernels(m, s);
+    if (st == FDCM_OK) st = upload_build_scene(m, scene_xyxy, n_lines, s);
     if (st == FDCM_OK) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("build: ") + cudaGetErrorString(e));
@@ -573,6 +601,7 @@ static fdcm_status rebuild_impl(fdcm_dt3* m, const float* scene_xyxy, int32_t n_
     if (fdcm_status st = get_stream(m->device, &s)) return st;
     fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
     if (st == FDCM_OK) st = run_build_kernels(m, s);
+    if (st == FDCM_OK) st = upload_build_scene(m, scene_xyxy, n_lines, s);
     if (st == FDCM_OK && wait) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("rebuild: ") + cudaGetErrorString(e));
