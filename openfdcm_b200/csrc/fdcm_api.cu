@@ -209,6 +209,8 @@ struct fdcm_dt3 {
     bool exact = true;
     int col_lo = 0, col_hi = 0;  // column range that can hold edge pixels (bbox of the shifted scene)
     int row_lo = 0, row_hi = 0;  // row range likewise
+    int tables_depth = -1;       // (depth, coeff) the slope table / propagation schedule / integral directions were built for
+    float tables_coeff = 0.f;
     bool row_literal = false;   // FDCM_ROW_LITERAL=1: use the literal row pass even in the exact regime (A/B testing)
     int n_lines = 0;
     std::vector<float> keys;
@@ -399,7 +401,8 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
         m->col_hi = (!(hi == hi) || hi > dm.W - 1) ? dm.W - 1 : (hi < 0.0 ? 0 : (int)hi);
     }
 
-    // tables
+    // tables: functions of (depth, coeff) only, kept across rebuilds of the same map
+    if (m->tables_depth != D || m->tables_coeff != m->params.dt3_coeff) {
     m->table = build_slope_table(m->keys.data(), D);
     if ((int)m->table.thr.size() > kMaxDepthDev + 8) return fail(FDCM_ERR_INVALID, "slope table too large");
     m->table_dev.n_thr = (int)m->table.thr.size();
@@ -418,6 +421,9 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
         m->integ.rx[d] = id.rx;
         m->integ.ry[d] = id.ry;
         m->integ.mode[d] = id.mode;
+    }
+    m->tables_depth = D;
+    m->tables_coeff = m->params.dt3_coeff;
     }
 
     // device allocations (grow-only)
