@@ -406,3 +406,50 @@ def test_real_asset_regression():
         top = fdcm.search_topk(g, tmpls, scene, fdcm.DefaultSearch(4, 10), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5), k=10)
         pen = orc.penalize(1, 1.5, want, orc.template_lengths(tmpls))
         assert np.array_equal(top, pen[np.lexsort((np.arange(len(pen)), pen["score"]))[:10]])
+
+
+def _special_scene(kind, w, h, rng):
+    """Geometries that stress the band kernels: a single line, lines on the borders of the extent (edges in the first /
+    last map row at padding 1), a dense corner cluster plus one far line, all lines in one orientation bin."""
+    if kind == 0:
+        return np.array([[w * 0.2], [h * 0.3], [w * 0.7], [h * 0.35]], F32)
+    if kind == 1:
+        ls = [[0, 0, w - 1, 0], [0, h - 1, w - 1, h - 1], [0, 0, 0, h - 1], [w - 1, 0, w - 1, h - 1], [w / 2, 0, w / 2, h - 1],
+              [0, h / 2, w - 1, h / 2]]
+        return np.array(ls, F32).T.copy()
+    if kind == 2:
+        s = synth_scene(max(w // 4, 80), max(h // 4, 60), 40, seed=int(rng.integers(1 << 30)), min_len=4.0)
+        return np.ascontiguousarray(np.concatenate([s, np.array([[w - 30], [h - 20], [w - 5], [h - 3]], F32)], axis=1), F32)
+    if kind == 3:
+        n = 25
+        cx, cy = rng.uniform(0, w - 1, n), rng.uniform(0, h - 1, n)
+        ln, th = rng.uniform(10, 0.3 * w, n), 0.3 + rng.uniform(-0.02, 0.02, n)
+        l = np.stack([cx - ln * np.cos(th) / 2, cy - ln * np.sin(th) / 2, cx + ln * np.cos(th) / 2, cy + ln * np.sin(th) / 2])
+        l[[0, 2]] = np.clip(l[[0, 2]], 0, w - 1)
+        l[[1, 3]] = np.clip(l[[1, 3]], 0, h - 1)
+        return np.ascontiguousarray(l, F32)
+    return synth_scene(w, h, int(rng.integers(3, 200)), seed=int(rng.integers(1 << 30)), max_len_frac=float(rng.uniform(0.3, 0.6)),
+                       min_len=4.0)
+
+
+@pytest.mark.parametrize("case", range(12))
+def test_randomised_scenes_bit_exact(case):
+    """Random sizes / paddings / special geometries, all three distances: full maps and full match lists bit-exact against
+    the oracle (scripts/fuzz_parity.py runs a longer sweep of the same kind)."""
+    rng = np.random.default_rng(1000 + case)
+    w, h = int(rng.integers(40, 700)), int(rng.integers(40, 500))
+    pad = float(rng.choice([1.0, 1.2, 1.5, 2.2]))
+    name = ["L2", "L2_SQUARED", "L1"][case % 3]
+    gd, od = DIST[name]
+    scene = _special_scene(case % 6, w, h, rng)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, pad, gd))
+    c = orc.Dt3Cpu(scene, 30, 5.0, pad, od)
+    assert (g.width, g.height) == (c.W, c.H)
+    for d in range(30):
+        assert np.array_equal(g.plane(d), c.plane(d)), f"plane {d} of case {case} ({name}, {w}x{h}, padding {pad})"
+    tm = synth_templates(6, 12, max(w, 100), seed=case)
+    got = fdcm.search_all(g, tm, scene, fdcm.DefaultSearch(3, 4), fdcm.BatchOptimize(10))
+    want = c.search(tm, scene, 3, 4, batch=10)
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.array_equal(got["score"], want["score"], equal_nan=True)
+    assert np.array_equal(got["transform"], want["transform"], equal_nan=True)
