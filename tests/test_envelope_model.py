@@ -1,0 +1,176 @@
+"""CPU model of the band distance-transform kernels (openfdcm_b200/csrc/dt_band_kernels.cu), checked against the oracle's
+literal restatement of _distanceTransformColumnPassL2 (core/imgproc.h:91-130).  It pins, without a GPU, the three
+arguments the CUDA kernels rest on:
+  * the integer stack algorithm (left / mirrored right stack) and the join of two stacks at their single crossing,
+  * the chained base values that reproduce the in-place aliasing of the reference's second loop,
+  * the candidate pruning of far bands: the survivors of a loose-pop pass over the row next to a plane's edge rows are a
+    superset of the owners of every farther row.
+Pure Python on small rows: this is a model of the algorithm, not the product."""
+import numpy as np
+import pytest
+
+from oracle import fdcm_oracle as orc
+
+BIG = 0xFFFF
+
+
+class Stack:
+    """entries [key = g^2 + v^2, v, bound]; bound = first owned pixel (left stack) or last owned pixel (right stack)"""
+
+    def __init__(self, loose=False):
+        self.e = []
+        self.slack = 1 if loose else 0
+
+    def take_over(self, v, key, wm1):
+        while self.e:
+            tk, tv, ts = self.e[-1]
+            n, dn = key - tk, 2 * (v - tv)
+            if n < (ts - self.slack) * dn:
+                self.e.pop()
+                continue
+            if n >= wm1 * dn:
+                return wm1 + 1
+            return n // dn + 1
+        return 0
+
+    def column(self, v, g, wm1):
+        key = g * g + v * v
+        start = self.take_over(v, key, wm1)
+        if start <= wm1:
+            self.e.append([key, v, start])
+
+    def column_rev(self, v, g, wm1):
+        key, end = g * g + v * v, wm1
+        while self.e:
+            tk, tv, ts = self.e[-1]
+            n, dn = tk - key, 2 * (tv - v)
+            if n >= (ts + self.slack) * dn:
+                self.e.pop()
+                continue
+            if n < 0:
+                return
+            end = n // dn
+            break
+        self.e.append([key, v, end])
+
+
+def joined_envelope(g, xsplit):
+    """two stacks + join, as dt_row_band_kernel does it; returns [(key, v, first owned pixel)] in ascending v"""
+    n, wm1 = len(g), len(g) - 1
+    left, right = Stack(), Stack()
+    for v in range(0, xsplit):
+        if g[v] != BIG:
+            left.column(v, int(g[v]), wm1)
+    for v in range(n - 1, xsplit - 1, -1):
+        if g[v] != BIG:
+            right.column_rev(v, int(g[v]), wm1)
+    r = right.e[::-1]
+    j, right_start = 0, 0
+    while j < len(r):
+        key, v, end = r[j]
+        j += 1
+        start = left.take_over(v, key, wm1)
+        if start <= end:
+            left.e.append([key, v, start])
+            right_start = end + 1
+            break
+    ent = [tuple(x) for x in left.e]
+    for key, v, end in r[j:]:
+        ent.append((key, v, right_start))
+        right_start = end + 1
+    return ent
+
+
+def fill(ent, n):
+    """RowFill: chained bases, then out(q) = base(owner) + (q - v)^2"""
+    if not ent:
+        return np.full(n, np.finfo(np.float32).max, np.float32)
+    base = []
+    for k, (key, v, s) in enumerate(ent):
+        f = key - v * v
+        if s > v:                      # vertex left of its own interval: it contributes the already written out(v)
+            j = k - 1
+            while ent[j][2] > v:
+                j -= 1
+            f = base[j] + (v - ent[j][1]) ** 2
+        base.append(f)
+    out, k = np.zeros(n, np.float64), 0
+    for q in range(n):
+        while k + 1 < len(ent) and ent[k + 1][2] <= q:
+            k += 1
+        out[q] = base[k] + (q - ent[k][1]) ** 2
+    return out.astype(np.float32)
+
+
+def literal(g):
+    fmax = np.finfo(np.float32).max
+    return orc.dt_pass_l2_1d(np.where(g == BIG, fmax, g.astype(np.float64) ** 2).astype(np.float32))
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_two_stack_join_and_chained_bases_match_the_literal_pass(seed):
+    rng = np.random.default_rng(seed)
+    for trial in range(250):
+        n = int(rng.integers(1, 300))
+        g = rng.integers(0, [3, 10, 50, 400, 2800, 40][trial % 6], n)
+        if trial % 3 == 0:
+            g = np.where(rng.random(n) < 0.7, BIG, g)
+        if trial % 7 == 0:
+            g = np.where(np.arange(n) < n // 3, g, BIG)
+        if trial % 11 == 0:
+            g = np.where(np.arange(n) > 2 * n // 3, g, BIG)
+        xsplit = int(rng.integers(0, n + 1))
+        got = fill(joined_envelope(g, xsplit), n)
+        assert np.array_equal(got, literal(g)), (seed, trial, n, xsplit)
+
+
+def _owners(g):
+    """columns that own at least one pixel of the row (strict single left stack)"""
+    st = Stack()
+    for v in range(len(g)):
+        if g[v] != BIG:
+            st.column(v, int(g[v]), len(g) - 1)
+    own = set()
+    for k, (_, v, s) in enumerate(st.e):
+        nxt = st.e[k + 1][2] if k + 1 < len(st.e) else len(g)
+        if nxt > s:
+            own.add(v)
+    return own
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_loose_pass_next_to_the_edge_rows_covers_every_farther_row(seed):
+    rng = np.random.default_rng(100 + seed)
+    w, h = int(rng.integers(20, 90)), int(rng.integers(30, 80))
+    mask = np.zeros((h, w), bool)
+    for _ in range(int(rng.integers(1, 7))):                       # a few short segments in the middle rows
+        x0, y0 = int(rng.integers(0, w)), int(rng.integers(h // 3, 2 * h // 3))
+        dx, dy = int(rng.integers(-12, 13)), int(rng.integers(-6, 7))
+        for t in np.linspace(0, 1, 30):
+            x, y = int(round(x0 + t * dx)), int(round(y0 + t * dy))
+            if 0 <= x < w and 0 <= y < h:
+                mask[y, x] = True
+    rows = np.flatnonzero(mask.any(1))
+    r_top, r_bot = int(rows[0]), int(rows[-1])
+    top = np.where(mask.any(0), mask.argmax(0), -1)                # first edge row per column
+    bot = np.where(mask.any(0), h - 1 - mask[::-1].argmax(0), -1)  # last edge row per column
+    for side, y_ref, far_rows in ((0, r_top - 1, range(r_top - 1, -1, -1)), (1, r_bot + 1, range(r_bot + 1, h))):
+        if y_ref < 0 or y_ref >= h:
+            continue
+        dist = lambda y: np.where(top >= 0, (top - y) if side == 0 else (y - bot), BIG)
+        # candidate pass as the kernel runs it: loose pops, left half ascending + right half descending, no join
+        g0, xs = dist(y_ref), w // 2
+        left, right = Stack(loose=True), Stack(loose=True)
+        for v in range(0, xs):
+            if g0[v] != BIG:
+                left.column(v, int(g0[v]), w - 1)
+        for v in range(w - 1, xs - 1, -1):
+            if g0[v] != BIG:
+                right.column_rev(v, int(g0[v]), w - 1)
+        cand = {e[1] for e in left.e} | {e[1] for e in right.e}
+        for y in far_rows:
+            g = dist(y)
+            assert _owners(g) <= cand, (seed, side, y)
+            # and the pruned row gives the same result as the full one
+            gp = np.where(np.isin(np.arange(w), list(cand)), g, BIG)
+            assert np.array_equal(fill(joined_envelope(gp, xs), w), literal(g)), (seed, side, y)
