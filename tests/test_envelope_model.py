@@ -174,3 +174,22 @@ def test_loose_pass_next_to_the_edge_rows_covers_every_farther_row(seed):
             # and the pruned row gives the same result as the full one
             gp = np.where(np.isin(np.arange(w), list(cand)), g, BIG)
             assert np.array_equal(fill(joined_envelope(gp, xs), w), literal(g)), (seed, side, y)
+
+
+def test_first_minimum_by_bit_pattern_order():
+    """search_warp_kernel picks the first minimum of a batch with a warp min-reduction over the float bit patterns
+    (batchoptimize.cpp:60 std::min_element on scores that are sums of absolute values): for non-negative floats the
+    unsigned order of the bits is the numeric order, so min over bits + lowest index among equals == the sequential scan
+    `if (s < bmin)`; batches that hold a NaN take the sequential path in the kernel."""
+    rng = np.random.default_rng(5)
+    for _ in range(2000):
+        n = int(rng.integers(1, 33))
+        s = rng.choice([0.0, 1.5, 3.25, 7.0, np.inf, 1e-30, 2.0 ** -140], n).astype(np.float32)
+        s[rng.random(n) < 0.3] = np.float32(rng.uniform(0, 10))
+        bmin, barg = s[0], 0
+        for j in range(1, n):
+            if s[j] < bmin:
+                bmin, barg = s[j], j
+        bits = s.view(np.uint32)
+        kmin = bits.min()
+        assert int(np.flatnonzero(bits == kmin)[0]) == barg and np.float32(bmin).view(np.uint32) == kmin
