@@ -194,7 +194,7 @@ def main():
         out = np.zeros(TOP_K, fdcm.MATCH_DTYPE)
         n = C.c_int64(0)
         p = fdcm._lib.SearchParams(MAX_T, MAX_S, BATCH, penalty.kind, penalty.tau, TOP_K, base, 0, 0.0, 0.0, 0.0, 0.0)
-        fdcm.check(L.fdcm_search_host(fm._h, h_lines.data_ptr(), h_off.data_ptr(), N_TMPL, None, 0,   # scene: the one just uploaded by the rebuild
+        fdcm.check(L.fdcm_search_host(fm._h, h_lines.data_ptr(), h_off.data_ptr(), N_TMPL, None, fdcm._lib.FDCM_SCENE_RESIDENT,   # scene: the one just uploaded by the rebuild
                                       C.byref(p), fdcm.ptr(out), TOP_K, C.byref(n)))
         return merge(out[: n.value])
 

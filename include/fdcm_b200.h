@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define FDCM_B200_ABI_VERSION 2
+#define FDCM_B200_ABI_VERSION 3
 
 typedef enum fdcm_status {
     FDCM_OK = 0,
@@ -155,8 +155,11 @@ fdcm_status fdcm_templates_lengths(const fdcm_templates* t, float* lengths);
 
 /* search(DefaultMatch, DefaultSearch, BatchOptimize|DefaultOptimize, featuremap, templates, scene)
  * (defaultmatch.cpp:32-89) [+ penalize + sort/top-k]. `scene_xyxy` is the ORIGINAL scene
- * (un-shifted), as in the reference. out: capacity records; *n_out = number written (or required
+ * (un-shifted), as in the reference; n_scene == 0 yields no matches (defaultmatch.cpp:40) and
+ * n_scene == FDCM_SCENE_RESIDENT (scene_xyxy ignored) searches the scene the map was built from, which is
+ * already resident on the device.  out: capacity records; *n_out = number written (or required
  * when FDCM_ERR_CAPACITY). */
+#define FDCM_SCENE_RESIDENT (-1)
 fdcm_status fdcm_search(const fdcm_dt3* map, const fdcm_templates* templates, const float* scene_xyxy, int32_t n_scene,
                         const fdcm_search_params* params, fdcm_match* out, int64_t capacity, int64_t* n_out);
 /* optimize(optimizer, templates, alignments, featuremap) (matching/optimizestrategy.h:62-64; BatchOptimize:
@@ -188,7 +191,8 @@ fdcm_status fdcm_concentric_search(const float* tmpl_xyxy, int32_t n_tmpl_lines,
 
 /* Parity hook: run the horizontal L2^2 pass (second _distanceTransformColumnPassL2 call, core/imgproc.h:91-130)
  * on n_rows arbitrary rows of u16 vertical distances g (0xFFFF = FLT_MAX), f = g*g.  literal = 1 selects the
- * literal stack kernel, 0 the exact-regime warp kernel.  out: n_rows x n floats (squared distances). */
+ * literal stack kernel (the path of maps with side > 2897), 2 the exact-regime band kernels (envelope + fill).
+ * out: n_rows x n floats (squared distances). */
 fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows, int32_t n, int32_t literal, int32_t device, float* out);
 
 /* Orientation bins (closestOrientation, dt3cpu.h:93-114, for the `depth` keys of dt3cpu.h:188-190) of n lines,

@@ -322,7 +322,7 @@ def _search_raw(featuremap, templates, scene, searcher, optimizer, penalty=None,
         1, searcher.max_scene_lines)
     out = np.zeros(max(cap, 1), MATCH_DTYPE)
     n = C.c_int64(0)
-    check(lib().fdcm_search(featuremap._h, tset._h, ptr(s), 0 if s is None else s.shape[0], C.byref(p), ptr(out),
+    check(lib().fdcm_search(featuremap._h, tset._h, ptr(s), _lib.FDCM_SCENE_RESIDENT if s is None else s.shape[0], C.byref(p), ptr(out),
                             out.shape[0], C.byref(n)))
     return out[: n.value]
 

@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libfdcm_b200.so")
 
 FDCM_OK = 0
 FDCM_ERR_INVALID, FDCM_ERR_CUDA, FDCM_ERR_NOMEM, FDCM_ERR_OUT_OF_RANGE, FDCM_ERR_CAPACITY = 1, 2, 3, 4, 5
+FDCM_SCENE_RESIDENT = -1   # n_scene value: search the scene the map was built from (resident on the device)
 
 MATCH_DTYPE = np.dtype([("tmpl_idx", "<i4"), ("score", "<f4"), ("transform", "<f4", (6,))])
 assert MATCH_DTYPE.itemsize == 32

@@ -113,115 +113,6 @@ __global__ void __launch_bounds__(256) raster_kernel(const float4* __restrict__ 
     for (int i = lane; i < size; i += 32) set_edge(mask, dm, plane, round_to_ll(lx.at(i)), round_to_ll(ly.at(i)));
 }
 
-// =============================================================================================
-// K2a: vertical pass on the binary mask, exact regime.
-// With a {0, FLT_MAX} input and 2*(side-1)^2 < 2^24 every quantity of the reference's first
-// _distanceTransformColumnPassL2 call (core/imgproc.h:91-130) is an exactly representable integer,
-// so its output is (distance to the nearest edge pixel in the column)^2; we store the distance
-// itself (u16; 0xFFFF = no edge in the column = FLT_MAX).  The same array feeds the L1 transform.
-// =============================================================================================
-__global__ void __launch_bounds__(128) dt_col_exact_kernel(const uint32_t* __restrict__ mask, MapDims dm,
-                                                           uint16_t* __restrict__ g) {
-    const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = blockIdx.y;
-    if (x >= dm.W) return;
-    const uint32_t* m = mask + (size_t)d * dm.H * dm.wwords + (x >> 5);
-    const uint32_t bit = 1u << (x & 31);
-    uint16_t* gp = g + (size_t)d * dm.plane_elems + x;
-    int last = -1;
-#pragma unroll 8
-    for (int y = 0; y < dm.H; ++y) {
-        if (m[(size_t)y * dm.wwords] & bit) last = y;
-        gp[(size_t)y * dm.pitch] = last < 0 ? kNoEdge16 : (uint16_t)(y - last);
-    }
-    int next = -1;
-#pragma unroll 8
-    for (int y = dm.H - 1; y >= 0; --y) {
-        if (m[(size_t)y * dm.wwords] & bit) next = y;
-        const uint16_t dn = next < 0 ? kNoEdge16 : (uint16_t)(next - y);
-        const uint16_t up = gp[(size_t)y * dm.pitch];
-        gp[(size_t)y * dm.pitch] = up < dn ? up : dn;
-    }
-}
-
-// K2a, tiled: one CTA per (plane, 64 columns).  Phase A transposes the mask into per-column 32-row bit words
-// (warp ballots), phase B scans the bands once per column for the nearest edge above / below each band, phase C
-// resolves every pixel with two bit scans (clz / ffs) and writes 128-byte row segments of u16 distances.
-__global__ void __launch_bounds__(256) dt_col_tiled_kernel(const uint32_t* __restrict__ mask, MapDims dm,
-                                                           uint16_t* __restrict__ g, int nbands) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* M = reinterpret_cast<uint32_t*>(smem_raw);                  // [nbands][64] column bit words
-    int32_t* up_before = reinterpret_cast<int32_t*>(M + (size_t)nbands * 64);   // [nbands][64] last edge row above the band
-    int32_t* dn_after = up_before + (size_t)nbands * 64;                       // [nbands][64] first edge row below the band
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    const int d = blockIdx.y;
-    const int w0 = blockIdx.x * 2;                                        // first mask word (32 columns each)
-    const uint32_t* mp = mask + (size_t)d * dm.H * dm.wwords;
-    // ---- A: transpose ----
-    for (int b = warp; b < nbands; b += nwarps) {
-        const int y = b * 32 + lane;
-        uint32_t a0 = 0, a1 = 0;
-        if (y < dm.H) {
-            a0 = mp[(size_t)y * dm.wwords + w0];
-            if (w0 + 1 < dm.wwords) a1 = mp[(size_t)y * dm.wwords + w0 + 1];
-        }
-        uint32_t c0 = 0, c1 = 0;
-#pragma unroll
-        for (int c = 0; c < 32; ++c) {
-            const uint32_t m0 = __ballot_sync(0xffffffffu, (a0 >> c) & 1u);
-            const uint32_t m1 = __ballot_sync(0xffffffffu, (a1 >> c) & 1u);
-            if (lane == c) { c0 = m0; c1 = m1; }
-        }
-        M[(size_t)b * 64 + lane] = c0;
-        M[(size_t)b * 64 + 32 + lane] = c1;
-    }
-    __syncthreads();
-    // ---- B: nearest edge row strictly above / below every band, per column ----
-    if (threadIdx.x < 64) {
-        const int c = threadIdx.x;
-        int last = -1;
-        for (int b = 0; b < nbands; ++b) {
-            up_before[(size_t)b * 64 + c] = last;
-            const uint32_t m = M[(size_t)b * 64 + c];
-            if (m) last = b * 32 + 31 - __clz(m);
-        }
-        int next = -1;
-        for (int b = nbands - 1; b >= 0; --b) {
-            dn_after[(size_t)b * 64 + c] = next;
-            const uint32_t m = M[(size_t)b * 64 + c];
-            if (m) next = b * 32 + __ffs(m) - 1;
-        }
-    }
-    __syncthreads();
-    // ---- C: per pixel ----
-    const int x = blockIdx.x * 64 + lane * 2;                             // this lane's two columns
-    if (x >= dm.pitch) return;
-    uint16_t* gp = g + (size_t)d * dm.plane_elems + x;
-    for (int b = warp; b < nbands; b += nwarps) {
-        const uint2 bits = *reinterpret_cast<const uint2*>(M + (size_t)b * 64 + lane * 2);
-        const int2 ub = *reinterpret_cast<const int2*>(up_before + (size_t)b * 64 + lane * 2);
-        const int2 da = *reinterpret_cast<const int2*>(dn_after + (size_t)b * 64 + lane * 2);
-        const int rows = min(32, dm.H - b * 32);
-        for (int r = 0; r < rows; ++r) {
-            const int y = b * 32 + r;
-            const uint32_t le = 0xFFFFFFFFu >> (31 - r), ge = 0xFFFFFFFFu << r;
-            uint32_t res = 0;
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-                const uint32_t m = k ? bits.y : bits.x;
-                const int upb = k ? ub.y : ub.x, dna = k ? da.y : da.x;
-                const uint32_t above = m & le, below = m & ge;
-                const int up = above ? (b * 32 + 31 - __clz(above)) : upb;
-                const int dn = below ? (b * 32 + __ffs(below) - 1) : dna;
-                unsigned dist = 0xFFFFu;
-                if (up >= 0) dist = (unsigned)(y - up);
-                if (dn >= 0) dist = min(dist, (unsigned)(dn - y));
-                res |= (dist & 0xFFFFu) << (16 * k);
-            }
-            *reinterpret_cast<uint32_t*>(gp + (size_t)y * dm.pitch) = res;
-        }
-    }
-}
 
 // general regime: materialise the {0, FLT_MAX} image (core/imgproc.h:174-175)
 __global__ void __launch_bounds__(256) mask_to_float_kernel(const uint32_t* __restrict__ mask, MapDims dm,
@@ -295,481 +186,6 @@ __global__ void __launch_bounds__(128) dt_pass_literal_kernel(const uint16_t* __
         const long long dq = (long long)q - v;
         const float src = (kFromG && v >= q) ? F(v) : out[(size_t)v * elem_stride];
         out[(size_t)q * elem_stride] = src + (float)(dq * dq);
-    }
-}
-
-// =============================================================================================
-// K2b (exact regime): horizontal pass of the L2 / L2^2 transform, one warp per row, row in shared memory.
-//
-// In the exact regime (2*(side-1)^2 < 2^24) every quantity of the reference's second
-// _distanceTransformColumnPassL2 call (core/imgproc.h:91-130) is an exactly representable integer, so
-//   (1) the envelope it builds is the true lower envelope of the parabolas f[v] + (q-v)^2, f = g^2, and the
-//       vertex that owns an integer q is the LEFTMOST argmin_v f[v] + (q-v)^2 (`while (z[k+1] < q)` keeps
-//       the left parabola on a tie; FLT_MAX columns never own a pixel);
-//   (2) its in-place second loop computes out[q] = (u < q ? out[u] : f[u]) + (q-u)^2 with u = owner(q),
-//       a sum of integers, exact in any order.
-// owner() is non-decreasing in q, so it is found by divide and conquer: the owner of the midpoint of an
-// interval lies between the owners of its end points (equal end owners resolve the whole interval).
-// Lanes take one query each; brackets longer than kCoopLen are scanned by the whole warp.  The chained
-// values are then resolved in place, 32 pixels at a time, exactly like the reference's left-to-right sweep.
-// =============================================================================================
-constexpr uint32_t kBigF = 0x3FFFFFFFu;   // stands for FLT_MAX: never wins against a finite parabola
-constexpr int kScanLen = 48;              // brackets up to this length are scanned linearly
-constexpr int kMaxBlocks = 96;            // 32-column blocks per row (n <= 2897 -> 91)
-
-// leftmost argmin of f[v] + (q-v)^2 over v in [lo, hi] by one lane.  Long brackets are pruned with the
-// per-32-column block minima (bmin: min f of the block, bpos: its leftmost position): a block can only hold
-// the owner if bmin + dist(q, block)^2 does not exceed the best cost already known.
-__device__ __forceinline__ int lane_owner(const uint32_t* f, const uint32_t* bmin, const uint16_t* bpos, int q, int lo, int hi) {
-    int d = q - lo;
-    uint32_t best = f[lo] + (uint32_t)(d * d);
-    int arg = lo;
-    if (hi - lo <= kScanLen) {
-        for (int v = lo + 1; v <= hi; ++v) {
-            d = q - v;
-            const uint32_t c = f[v] + (uint32_t)(d * d);
-            if (c < best) { best = c; arg = v; }
-        }
-        return arg;
-    }
-    // upper bound from valid candidates: lo, hi and the minima of the blocks strictly inside the bracket
-    d = q - hi;
-    uint32_t U = min(best, f[hi] + (uint32_t)(d * d));
-    const int b_lo = lo >> 5, b_hi = hi >> 5;
-    for (int b = b_lo + 1; b < b_hi; ++b) {
-        d = q - (int)bpos[b];
-        U = min(U, bmin[b] + (uint32_t)(d * d));
-    }
-    // scan, left to right, every block whose lower bound does not exceed the bound (ties must be scanned)
-    best = 0xFFFFFFFFu;
-    for (int b = b_lo; b <= b_hi; ++b) {
-        const int v0 = max(b << 5, lo), v1 = min((b << 5) + 31, hi);
-        const int dist = q < v0 ? v0 - q : (q > v1 ? q - v1 : 0);
-        if (bmin[b] + (uint32_t)(dist * dist) > U) continue;
-        for (int v = v0; v <= v1; ++v) {
-            d = q - v;
-            const uint32_t c = f[v] + (uint32_t)(d * d);
-            if (c < best) { best = c; arg = v; }
-        }
-        U = min(U, best);
-    }
-    return arg;
-}
-
-// leftmost argmin of f[v] + (q-v)^2 over v in [lo, hi], all 32 lanes cooperating (uniform arguments).
-// Blocks whose lower bound bmin + dist(q, block)^2 exceeds the best known cost are skipped.
-__device__ int coop_owner(const uint32_t* f, const uint32_t* bmin, const uint16_t* bpos, int q, int lo, int hi, int lane) {
-    unsigned long long best = ~0ull;
-    if (hi - lo < 96) {
-        for (int v = lo + lane; v <= hi; v += 32) {
-            const int d = q - v;
-            const unsigned long long key = ((unsigned long long)(f[v] + (uint32_t)(d * d)) << 16) | (unsigned)v;
-            best = key < best ? key : best;
-        }
-    } else {
-        const int b_lo = lo >> 5, b_hi = hi >> 5;
-        int d = q - lo;
-        uint32_t U = f[lo] + (uint32_t)(d * d);
-        d = q - hi;
-        U = min(U, f[hi] + (uint32_t)(d * d));
-        for (int b = b_lo + 1 + lane; b < b_hi; b += 32) {   // interior blocks: their minima are valid candidates
-            d = q - (int)bpos[b];
-            U = min(U, bmin[b] + (uint32_t)(d * d));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) U = min(U, __shfl_xor_sync(0xffffffffu, U, o));
-        for (int b0 = b_lo; b0 <= b_hi; b0 += 32) {
-            const int b = b0 + lane;
-            bool surv = false;
-            if (b <= b_hi) {
-                const int v0 = max(b << 5, lo), v1 = min((b << 5) + 31, hi);
-                const int dist = q < v0 ? v0 - q : (q > v1 ? q - v1 : 0);
-                surv = bmin[b] + (uint32_t)(dist * dist) <= U;   // ties must be scanned (leftmost argmin)
-            }
-            unsigned todo = __ballot_sync(0xffffffffu, surv);
-            while (todo) {
-                const int v = ((b0 + __ffs(todo) - 1) << 5) + lane;
-                todo &= todo - 1;
-                if (v >= lo && v <= hi) {
-                    d = q - v;
-                    const unsigned long long key = ((unsigned long long)(f[v] + (uint32_t)(d * d)) << 16) | (unsigned)v;
-                    best = key < best ? key : best;
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-        best = other < best ? other : best;
-    }
-    return (int)(best & 0xFFFFu);
-}
-
-// owners of q and q+1 over [lo, hi] in one cooperative pass (shared loads and block pruning);
-// (q+1-v)^2 = (q-v)^2 + 2(q-v) + 1
-__device__ void coop_owner_pair(const uint32_t* f, const uint32_t* bmin, const uint16_t* bpos, int q, int lo, int hi, int lane,
-                                int& w1, int& w2) {
-    unsigned long long best1 = ~0ull, best2 = ~0ull;
-    auto eval = [&](int v) {
-        const int d = q - v;
-        const uint32_t c1 = f[v] + (uint32_t)(d * d);
-        const uint32_t c2 = (uint32_t)((int)c1 + 2 * d + 1);
-        const unsigned long long k1 = ((unsigned long long)c1 << 16) | (unsigned)v, k2 = ((unsigned long long)c2 << 16) | (unsigned)v;
-        best1 = k1 < best1 ? k1 : best1;
-        best2 = k2 < best2 ? k2 : best2;
-    };
-    if (hi - lo < 96) {
-        for (int v = lo + lane; v <= hi; v += 32) eval(v);
-    } else {
-        const int b_lo = lo >> 5, b_hi = hi >> 5;
-        int d = q - lo;
-        uint32_t c = f[lo] + (uint32_t)(d * d);
-        uint32_t U1 = c, U2 = (uint32_t)((int)c + 2 * d + 1);
-        d = q - hi;
-        c = f[hi] + (uint32_t)(d * d);
-        U1 = min(U1, c);
-        U2 = min(U2, (uint32_t)((int)c + 2 * d + 1));
-        for (int b = b_lo + 1 + lane; b < b_hi; b += 32) {
-            d = q - (int)bpos[b];
-            c = bmin[b] + (uint32_t)(d * d);
-            U1 = min(U1, c);
-            U2 = min(U2, (uint32_t)((int)c + 2 * d + 1));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            U1 = min(U1, __shfl_xor_sync(0xffffffffu, U1, o));
-            U2 = min(U2, __shfl_xor_sync(0xffffffffu, U2, o));
-        }
-        for (int b0 = b_lo; b0 <= b_hi; b0 += 32) {
-            const int b = b0 + lane;
-            bool surv = false;
-            if (b <= b_hi) {
-                const int v0 = max(b << 5, lo), v1 = min((b << 5) + 31, hi);
-                const int dist1 = q < v0 ? v0 - q : (q > v1 ? q - v1 : 0);
-                const int dist2 = q + 1 < v0 ? v0 - q - 1 : (q + 1 > v1 ? q + 1 - v1 : 0);
-                surv = bmin[b] + (uint32_t)(dist1 * dist1) <= U1 || bmin[b] + (uint32_t)(dist2 * dist2) <= U2;
-            }
-            unsigned todo = __ballot_sync(0xffffffffu, surv);
-            while (todo) {
-                const int v = ((b0 + __ffs(todo) - 1) << 5) + lane;
-                todo &= todo - 1;
-                if (v >= lo && v <= hi) eval(v);
-            }
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long o1 = __shfl_xor_sync(0xffffffffu, best1, o), o2 = __shfl_xor_sync(0xffffffffu, best2, o);
-        best1 = o1 < best1 ? o1 : best1;
-        best2 = o2 < best2 ? o2 : best2;
-    }
-    w1 = (int)(best1 & 0xFFFFu);
-    w2 = (int)(best2 & 0xFFFFu);
-}
-
-// leftmost argmin over a short bracket by one lane
-__device__ __forceinline__ int scan_owner(const uint32_t* f, int q, int lo, int hi) {
-    int d = q - lo;
-    uint32_t best = f[lo] + (uint32_t)(d * d);
-    int arg = lo;
-    for (int v = lo + 1; v <= hi; ++v) {
-        d = q - v;
-        const uint32_t c = f[v] + (uint32_t)(d * d);
-        if (c < best) { best = c; arg = v; }
-    }
-    return arg;
-}
-
-constexpr int kQueueCap = 256;   // intervals in flight per row (power of two)
-constexpr uint16_t kUnknown = 0xFFFFu;
-
-// Interval refinement.  pt[q] holds the owner of q at "known" pixels (0xFFFF elsewhere).  An interval (a, b) of known
-// pixels with owners oa != ob is split at the crossing x* of the two parabolas oa, ob (the last pixel where oa is
-// not worse): because every other parabola minus that two-parabola envelope is convex piecewise linear with its
-// minimum at the crossing, a third owner can exist inside (a, b) only if it already wins at x* or x*+1.  So the
-// owners of x* and x*+1 (searched over [oa, ob] only, owners are monotone) either certify the boundary or split
-// the interval further.  Work is proportional to the number of owner runs, not to the row length.
-// Only the columns [win_lo, win_lo + win_w) (multiples of 32; the scene's column range) can hold edges, so only they
-// need a slot in the f / out array; pixels outside are never an owner and are written straight to global memory.
-__global__ void __launch_bounds__(128) dt_row_exact_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
-                                                           MapDims dm, int n_rows_total, int win_lo, int win_w) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = dm.W;
-    // per warp: fwin[win_w] u32 | bmin[96] u32 | queue[kQueueCap] u32 | pt[pitch] u16 | bpos[96] u16
-    const size_t per_warp = (size_t)win_w * 4 + (size_t)dm.pitch * 2 + kMaxBlocks * 6 + kQueueCap * 4;
-    unsigned char* base = smem_raw + (size_t)warp * per_warp;
-    uint32_t* fwin = reinterpret_cast<uint32_t*>(base);
-    uint32_t* f = fwin - win_lo;                 // absolute column index; only dereferenced inside the window
-    uint32_t* bmin = fwin + win_w;
-    uint32_t* queue = bmin + kMaxBlocks;
-    uint16_t* pt = reinterpret_cast<uint16_t*>(queue + kQueueCap);
-    uint16_t* bpos = pt + dm.pitch;
-    const int win_hi = win_lo + win_w;           // exclusive
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp;   // row of the [D*H][pitch] stack of planes
-    if (row >= n_rows_total) return;
-    const uint16_t* gin = g + (size_t)row * dm.pitch;
-    float* out = planes + (size_t)row * dm.pitch;
-
-    // ---- load g, f = g^2; first / last finite column; clear pt ----
-    int cmin = 0x7fffffff, cmax = -1;
-    for (int x = lane * 2; x < dm.pitch; x += 64) *reinterpret_cast<uint32_t*>(pt + x) = 0xFFFFFFFFu;
-    for (int x = win_lo + lane * 2; x < win_hi; x += 64) {
-        const uint32_t two = *reinterpret_cast<const uint32_t*>(gin + x);
-        const uint32_t g0 = (x < n) ? (two & 0xFFFFu) : kNoEdge16, g1 = (x + 1 < n) ? (two >> 16) : kNoEdge16;
-        f[x] = g0 == kNoEdge16 ? kBigF : g0 * g0;
-        f[x + 1] = g1 == kNoEdge16 ? kBigF : g1 * g1;
-        if (g0 != kNoEdge16) { cmin = min(cmin, x); cmax = max(cmax, x); }
-        if (g1 != kNoEdge16) { cmin = min(cmin, x + 1); cmax = max(cmax, x + 1); }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        cmin = min(cmin, __shfl_xor_sync(0xffffffffu, cmin, o));
-        cmax = max(cmax, __shfl_xor_sync(0xffffffffu, cmax, o));
-    }
-    if (cmax < 0) {   // no edge pixel in this plane: the row stays FLT_MAX (imgproc.h:174)
-        for (int x = lane; x < n; x += 32) out[x] = FLT_MAX;
-        return;
-    }
-    __syncwarp();
-    // ---- per-block minima (lane = block, rotated column order: conflict-free) ----
-    for (int b = (win_lo >> 5) + lane; b < (win_hi >> 5); b += 32) {
-        uint32_t m = 0xFFFFFFFFu;
-        int pos = 0;
-        for (int i = 0; i < 32; ++i) {
-            const int c = (i + lane) & 31;
-            const uint32_t v = f[(b << 5) + c];
-            if (v < m || (v == m && c < pos)) { m = v; pos = c; }
-        }
-        bmin[b] = m;
-        bpos[b] = (uint16_t)((b << 5) + pos);
-    }
-    __syncwarp();
-
-    // ---- owners of the two end pixels, then breadth-first interval refinement ----
-    bool overflow = false;
-    {
-        const int o0 = coop_owner(f, bmin, bpos, 0, cmin, cmax, lane);
-        const int o1 = (n > 1) ? coop_owner(f, bmin, bpos, n - 1, o0, cmax, lane) : o0;
-        if (lane == 0) {
-            pt[0] = (uint16_t)o0;
-            pt[n - 1] = (uint16_t)o1;
-            queue[0] = (uint32_t)(n - 1) << 16;   // interval (a = 0, b = n-1): a in the low half, b in the high half
-        }
-    }
-    __syncwarp();
-    unsigned head = 0, tail = (n > 1) ? 1u : 0u;   // uniform across the warp
-    while (head != tail) {
-        const unsigned cnt = min(32u, tail - head);
-        const bool act = (unsigned)lane < cnt;
-        int a = 0, b = 0, oa = 0, ob = 0;
-        if (act) {
-            const uint32_t e = queue[(head + lane) & (kQueueCap - 1)];
-            a = (int)(e & 0xFFFFu);
-            b = (int)(e >> 16);
-            oa = pt[a];
-            ob = pt[b];
-        }
-        head += cnt;
-        // an interval needs work only if its end owners differ and it has interior pixels
-        const bool work = act && oa != ob && b > a + 1;
-        int x = 0, w1 = 0, w2 = 0;
-        bool is_long = false;
-        if (work) {
-            // last pixel where parabola oa is not worse than ob: floor((f_b - f_a + ob^2 - oa^2) / (2 (ob - oa)))
-            const int num = (int)f[ob] - (int)f[oa] + ob * ob - oa * oa;
-            const int den = 2 * (ob - oa);
-            int xs = num / den;
-            if (num % den != 0 && num < 0) --xs;
-            x = min(max(xs, a), b - 1);
-            is_long = (ob - oa) > kScanLen;
-            if (!is_long) {
-                w1 = (x == a) ? oa : scan_owner(f, x, oa, ob);
-                w2 = (x + 1 == b) ? ob : scan_owner(f, x + 1, w1, ob);
-            }
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, is_long);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int xq = __shfl_sync(0xffffffffu, x, src);
-            const int la = __shfl_sync(0xffffffffu, a, src), lb = __shfl_sync(0xffffffffu, b, src);
-            const int l2 = __shfl_sync(0xffffffffu, oa, src), h2 = __shfl_sync(0xffffffffu, ob, src);
-            int r1, r2;
-            if (xq == la) {
-                r1 = l2;
-                r2 = (xq + 1 == lb) ? h2 : coop_owner(f, bmin, bpos, xq + 1, l2, h2, lane);
-            } else if (xq + 1 == lb) {
-                r2 = h2;
-                r1 = coop_owner(f, bmin, bpos, xq, l2, h2, lane);
-            } else {
-                coop_owner_pair(f, bmin, bpos, xq, l2, h2, lane, r1, r2);
-            }
-            if (lane == src) { w1 = r1; w2 = r2; }
-        }
-        // publish the two new known pixels and enqueue the children that still straddle a boundary
-        bool c1 = false, c2 = false;
-        if (work) {
-            pt[x] = (uint16_t)w1;
-            pt[x + 1] = (uint16_t)w2;
-            c1 = (w1 != oa) && (x > a + 1);
-            c2 = (w2 != ob) && (b > x + 2);
-        }
-        const unsigned m1 = __ballot_sync(0xffffffffu, c1), m2 = __ballot_sync(0xffffffffu, c2);
-        const unsigned n1 = __popc(m1), n2 = __popc(m2);
-        if (tail - head + n1 + n2 > (unsigned)kQueueCap) { overflow = true; break; }
-        const unsigned lt = (1u << lane) - 1u;
-        if (c1) queue[(tail + __popc(m1 & lt)) & (kQueueCap - 1)] = (uint32_t)a | ((uint32_t)x << 16);
-        if (c2) queue[(tail + n1 + __popc(m2 & lt)) & (kQueueCap - 1)] = (uint32_t)(x + 1) | ((uint32_t)b << 16);
-        tail += n1 + n2;
-        __syncwarp();
-    }
-    if (overflow) {
-        // more than kQueueCap open intervals (very dense rows): plain divide and conquer over every pixel
-        __syncwarp();
-        for (int q = 31 + 32 * lane; q < n; q += 1024) pt[q] = (uint16_t)lane_owner(f, bmin, bpos, q, cmin, cmax);
-        __syncwarp();
-        for (int s = 16; s >= 1; s >>= 1) {
-            for (int q = s - 1 + 2 * s * lane; q < n; q += 64 * s) {
-                const int lo = (q - s >= 0) ? pt[q - s] : cmin;
-                const int hi = (q + s < n) ? pt[q + s] : cmax;
-                pt[q] = (uint16_t)((lo == hi) ? lo : lane_owner(f, bmin, bpos, q, lo, hi));
-            }
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-
-    // ---- chained values, in place, 32 pixels at a time (imgproc.h:122-128 incl. its aliasing) ----
-    int carry = 0;   // owner of the last known pixel of the previous chunks (pixel 0 is always known)
-    for (int x0 = 0; x0 < n; x0 += 32) {
-        const int q = x0 + lane;
-        const bool act = q < n;
-        // owner(q) = owner of the nearest known pixel at or left of q
-        const unsigned pv = act ? pt[q] : kUnknown;
-        const unsigned known = __ballot_sync(0xffffffffu, pv != kUnknown);
-        if (known == 0) {
-            // whole chunk inside one run (owner = carry): one broadcast read, no dependencies.  If the owner pixel is
-            // in this chunk it owns itself, so its slot is rewritten with the same value (f[carry] + 0)
-            if (act) {
-                const int dd = q - carry;
-                const uint32_t vv = f[carry] + (uint32_t)(dd * dd);
-                out[q] = (float)vv;
-                if (q >= win_lo && q < win_hi) f[q] = vv;
-            }
-            __syncwarp();
-            continue;
-        }
-        const unsigned le = known & (0xFFFFFFFFu >> (31 - lane));
-        const int srcl = le ? 31 - __clz(le) : 0;
-        const int ul = __shfl_sync(0xffffffffu, (int)pv, srcl);
-        const int u = le ? ul : carry;
-        if (known) carry = __shfl_sync(0xffffffffu, (int)pv, 31 - __clz(known));
-        const int d = q - u;
-        const uint32_t add = (uint32_t)(d * d);
-        uint32_t val = 0;
-        bool done = !act;
-        if (act && (u >= q || u < x0)) {   // right of q (not yet overwritten) or an earlier, finished chunk
-            val = f[u] + add;
-            done = true;
-        }
-        // owners inside this chunk and left of q: wait for that lane
-        unsigned pending = __ballot_sync(0xffffffffu, !done);
-        while (pending) {
-            const int src = act ? max(u - x0, 0) : 0;
-            const uint32_t sv = __shfl_sync(0xffffffffu, val, src);
-            const unsigned dn = __ballot_sync(0xffffffffu, done);
-            if (!done && ((dn >> src) & 1u)) {
-                val = sv + add;
-                done = true;
-            }
-            pending = __ballot_sync(0xffffffffu, !done);
-        }
-        __syncwarp();
-        if (act) {
-            out[q] = (float)val;                              // < 2^24: exact in fp32
-            if (q >= win_lo && q < win_hi) f[q] = val;        // only window columns can be referenced again
-        }
-        __syncwarp();
-    }
-}
-
-// K2b (L1): second pass of the L1 transform (core/imgproc.h:137-146,178-184) along x on the u16
-// vertical distance; integers are exact, so min-plus order is irrelevant.
-__global__ void __launch_bounds__(128) dt_row_l1_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
-                                                        MapDims dm) {
-    const int y = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = blockIdx.y;
-    if (y >= dm.H) return;
-    const size_t base = (size_t)d * dm.plane_elems + (size_t)y * dm.pitch;
-    const uint16_t* gin = g + base;
-    int* tmp = reinterpret_cast<int*>(planes + base);
-    float* out = planes + base;
-    const int BIG = 1 << 28;
-    int cur = BIG;
-    for (int x = 0; x < dm.W; ++x) {
-        const int gv = gin[x] == kNoEdge16 ? BIG : (int)gin[x];
-        cur = min(gv, cur + 1);
-        tmp[x] = cur;
-    }
-    cur = BIG;
-    for (int x = dm.W - 1; x >= 0; --x) {
-        cur = min(tmp[x], cur + 1);
-        out[x] = cur >= (BIG >> 1) ? FLT_MAX : (float)cur;
-    }
-}
-
-// K2b (L1), warp per row: out[x] = min(x + min_{v<=x}(g[v]-v), -x + min_{v>=x}(g[v]+v)) with warp prefix / suffix
-// min scans (integers: exact); the forward result is parked in shared memory between the two sweeps.
-__global__ void __launch_bounds__(128) dt_row_l1_warp_kernel(const uint16_t* __restrict__ g, float* __restrict__ planes,
-                                                             MapDims dm, int n_rows_total) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int* fwd = reinterpret_cast<int*>(smem_raw) + (size_t)warp * dm.pitch;
-    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (row >= n_rows_total) return;
-    const int n = dm.W;
-    const uint16_t* gin = g + (size_t)row * dm.pitch;
-    float* out = planes + (size_t)row * dm.pitch;
-    const int BIG = 1 << 28;
-    int carry = BIG;   // min over previous chunks of g[v] - v
-    for (int x0 = 0; x0 < n; x0 += 32) {
-        const int x = x0 + lane;
-        int a = BIG;
-        if (x < n) {
-            const int gv = gin[x];
-            a = gv == kNoEdge16 ? BIG : gv - x;
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, a, o);
-            if (lane >= o) a = min(a, t);
-        }
-        a = min(a, carry);
-        if (x < n) fwd[x] = a;
-        carry = __shfl_sync(0xffffffffu, a, 31);
-    }
-    __syncwarp();
-    carry = BIG;       // min over later chunks of g[v] + v
-    for (int x0 = ((n - 1) >> 5) << 5; x0 >= 0; x0 -= 32) {
-        const int x = x0 + lane;
-        int b = BIG;
-        if (x < n) {
-            const int gv = gin[x];
-            b = gv == kNoEdge16 ? BIG : gv + x;
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_down_sync(0xffffffffu, b, o);
-            if (lane + o < 32) b = min(b, t);
-        }
-        b = min(b, carry);
-        if (x < n) {
-            const int v = min(fwd[x] + x, b - x);
-            out[x] = v >= (BIG >> 1) ? FLT_MAX : (float)v;
-        }
-        carry = __shfl_sync(0xffffffffu, b, 0);
     }
 }
 
@@ -1149,23 +565,6 @@ void launch_raster(const float* d_lines, const int32_t* d_bins, int n_lines, con
                                                                    dm, d_mask);
 }
 
-void launch_dt_col_exact(const uint32_t* d_mask, const MapDims& dm, uint16_t* d_g, cudaStream_t s) {
-    const int nbands = (dm.H + 31) / 32;
-    const size_t smem = (size_t)nbands * 64 * 12;
-    if (smem <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(dt_col_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
-        dim3 grid((dm.wwords + 1) / 2, dm.D);
-        dt_col_tiled_kernel<<<grid, 256, smem, s>>>(d_mask, dm, d_g, nbands);
-        return;
-    }
-    dim3 grid(cdiv(dm.W, 128), dm.D);   // very tall maps: one thread per column, two sweeps
-    dt_col_exact_kernel<<<grid, 128, 0, s>>>(d_mask, dm, d_g);
-}
-
 void launch_mask_to_float(const uint32_t* d_mask, const MapDims& dm, float* d_planes, cudaStream_t s) {
     const size_t total = (size_t)dm.D * dm.plane_elems;
     mask_to_float_kernel<<<cdiv(total, 256), 256, 0, s>>>(d_mask, dm, d_planes);
@@ -1182,46 +581,6 @@ void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, f
         dt_pass_literal_kernel<true><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
     else
         dt_pass_literal_kernel<false><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
-}
-
-void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, int col_lo, int col_hi, cudaStream_t s) {
-    // column window that can hold edge pixels, widened to multiples of 32
-    int win_lo = (col_lo < 0 ? 0 : col_lo) & ~31;
-    int win_hi = ((col_hi >= dm.W ? dm.W - 1 : col_hi) + 32) & ~31;
-    if (win_hi > dm.pitch) win_hi = dm.pitch;
-    if (win_hi <= win_lo) { win_lo = 0; win_hi = dm.pitch; }
-    const int win_w = win_hi - win_lo;
-    const size_t per_warp = (size_t)win_w * 4 + (size_t)dm.pitch * 2 + 96 * 6 + 256 * 4;
-    // as many rows in flight per SM as shared memory allows (227 KB, 1 KB reserved per CTA)
-    int warps = 4;
-    int best_rows = 0;
-    for (int w = 1; w <= 4; ++w) {
-        const int ctas = (int)((227 * 1024) / (per_warp * w + 1024));
-        if (ctas * w > best_rows) { best_rows = ctas * w; warps = w; }
-    }
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(dt_row_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        attr_set = true;
-    }
-    const int rows = dm.D * dm.H;
-    dt_row_exact_kernel<<<cdiv(rows, warps), warps * 32, per_warp * warps, s>>>(d_g, d_planes, dm, rows, win_lo, win_w);
-}
-
-void launch_dt_row_l1(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s) {
-    const size_t per_warp = (size_t)dm.pitch * 4;
-    if (per_warp * 4 <= 200 * 1024) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(dt_row_l1_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-            attr_set = true;
-        }
-        const int rows = dm.D * dm.H;
-        dt_row_l1_warp_kernel<<<cdiv(rows, 4), 128, per_warp * 4, s>>>(d_g, d_planes, dm, rows);
-        return;
-    }
-    dim3 grid(cdiv(dm.H, 128), dm.D);
-    dt_row_l1_kernel<<<grid, 128, 0, s>>>(d_g, d_planes, dm);
 }
 
 void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s) {
@@ -1252,20 +611,16 @@ void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& i
     }
     if (any_y) integral_ymajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
     if (any_x) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(integral_xmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(4 * 2 * kTileRows * kVecPitch * sizeof(float)));
-            cudaFuncSetAttribute(integral_xmajor_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(4 * 2 * kTileRows * kTilePitch * sizeof(float)));
-            attr_set = true;
+        // (per call: the attribute is per device and a process may drive several devices)
+        if (dm.W % 4 == 0) {
+            const size_t smem = (size_t)4 * 2 * kTileRows * kVecPitch * sizeof(float);
+            cudaFuncSetAttribute(integral_xmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            integral_xmajor_kernel<<<grid, 128, smem, s>>>(d_planes, dm, ip, d_rtab, rlen);
+        } else {   // widths that are no multiple of 4 floats: the 4-byte staging variant
+            const size_t smem = (size_t)4 * 2 * kTileRows * kTilePitch * sizeof(float);
+            cudaFuncSetAttribute(integral_xmajor_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            integral_xmajor_scalar_kernel<<<grid, 128, smem, s>>>(d_planes, dm, ip, d_rtab, rlen);
         }
-        static const bool force_scalar = [] { const char* e = getenv("FDCM_INTEGRAL_SCALAR"); return e && e[0] == '1'; }();
-        if (dm.W % 4 == 0 && !force_scalar)
-            integral_xmajor_kernel<<<grid, 128, (size_t)4 * 2 * kTileRows * kVecPitch * sizeof(float), s>>>(d_planes, dm, ip, d_rtab, rlen);
-        else
-            integral_xmajor_scalar_kernel<<<grid, 128, (size_t)4 * 2 * kTileRows * kTilePitch * sizeof(float), s>>>(d_planes, dm, ip, d_rtab,
-                                                                                                                 rlen);
     }
 }
 

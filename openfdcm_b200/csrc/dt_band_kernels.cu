@@ -884,11 +884,8 @@ void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info,
     const int nbands = dt_band_count(dm);
     const size_t smem = (size_t)nbands * 64 * 6;
     dim3 grid((dm.wwords + 1) / 2, dm.D);
-    static size_t attr_smem = 48 * 1024;
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(dt_col_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
-    }
+    // (set per call: the attribute is per device and a process may drive several devices)
+    if (smem > 48 * 1024) cudaFuncSetAttribute(dt_col_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dt_col_band_kernel<<<grid, 256, smem, s>>>(d_mask, dm, reinterpret_cast<uint2*>(d_info), nbands, row_range);
 }
 
@@ -908,14 +905,13 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
     const int nbands = dt_band_count(dm);
     // split column: middle of the window that can hold edge pixels, on a 32-column boundary
     const int xsplit = min(dm.pitch, max(0, ((ws.win_lo + ws.win_lo + ws.maxdepth) / 2) & ~31));
-    static const bool no_prune = [] { const char* e = getenv("FDCM_NO_PRUNE"); return e && e[0] == '1'; }();
     int band_lo = (row_lo < 0 ? 0 : row_lo) >> 5, band_hi = (row_hi >= dm.H ? dm.H - 1 : row_hi) >> 5;
     if (band_hi < band_lo || band_hi >= nbands) { band_lo = 0; band_hi = nbands - 1; }
     if (d_g) {
         dt_row_band_kernel<true><<<(unsigned)(dm.D * nbands), 64, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
                                                                           BandAux{nullptr, nullptr, nullptr}, 0, band_lo, band_hi);
     } else {
-        const int n_cand = no_prune ? 0 : 2 * dm.D;
+        const int n_cand = 2 * dm.D;
         dt_row_band_kernel<false><<<(unsigned)(dm.D * nbands + n_cand), 64, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
                                                                                     ws.spill, ws.maxdepth, ws.row_k, xsplit,
                                                                                     band_aux(dm, d_ws, ws.maxdepth), n_cand, band_lo, band_hi);
@@ -935,11 +931,7 @@ void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, in
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     using C = FPConfig<30>;
     const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(dt_fill_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_set = true;
-    }
+    cudaFuncSetAttribute(dt_fill_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dt_fill_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, ws.maxdepth, pp, sqrt_first ? 1 : 0);
 }
 
@@ -953,11 +945,7 @@ void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& d
 void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& dm, const PropParams& pp, cudaStream_t s) {
     using C = FPConfig<30>;
     const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch >> 5) + 1) * sizeof(int);
-    static size_t attr_smem = 0;
-    if (smem > attr_smem) {
-        cudaFuncSetAttribute(dt_l1_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_smem = smem;
-    }
+    cudaFuncSetAttribute(dt_l1_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dt_l1_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(reinterpret_cast<const uint2*>(d_info), d_planes, dm, dt_band_count(dm), pp);
 }
 

@@ -211,7 +211,6 @@ struct fdcm_dt3 {
     int row_lo = 0, row_hi = 0;  // row range likewise
     int tables_depth = -1;       // (depth, coeff) the slope table / propagation schedule / integral directions were built for
     float tables_coeff = 0.f;
-    bool row_literal = false;   // FDCM_ROW_LITERAL=1: use the literal row pass even in the exact regime (A/B testing)
     int n_lines = 0;
     std::vector<float> keys;
     std::vector<int32_t> scene_bins;
@@ -219,10 +218,8 @@ struct fdcm_dt3 {
     SlopeTableDev table_dev{};
     PropParams prop{};
     IntegralParams integ{};
-    DevBuf planes, mask, g, stack, lines, bins, rtab, band_info, band_spill;
+    DevBuf planes, mask, stack, lines, bins, rtab, band_info, band_spill;
     bool band_path = false, band_l1 = false;   // which distance-transform formulation this map uses (set by prepare)
-    bool fuse_fill = true;      // FDCM_FUSE_FILL=0: separate fill and propagate kernels (A/B testing)
-    int row_mode = 0;           // exact-regime row pass: 0 = band kernel (default), 1 = literal, 2 = warp-per-row interval refinement
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
     mutable DevBuf s_scene, s_sorted_len, s_sorted_idx, s_hyp_off, s_rec, s_valid, s_hyp, s_counters, s_topk_score, s_topk_idx,
@@ -246,7 +243,7 @@ struct fdcm_dt3 {
 
     ~fdcm_dt3() {
         cudaSetDevice(device);
-        for (DevBuf* b : {&planes, &mask, &g, &stack, &lines, &bins, &rtab, &band_info, &band_spill, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
+        for (DevBuf* b : {&planes, &mask, &stack, &lines, &bins, &rtab, &band_info, &band_spill, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
                           &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n, &s_keys, &s_keys2, &s_idx,
                           &s_perm, &s_sort_tmp})
             b->release();
@@ -257,6 +254,10 @@ struct fdcm_dt3 {
     }
     void destroy_host_tset();
 };
+
+// largest supported map side: the band kernels keep one column of band records per CTA in shared memory (H <= 17056)
+// and u16 fields hold column indices; 16384^2 x 30 planes is already a 32 GB map
+constexpr int64_t kMaxSide = 16384;
 
 struct SceneFilter { bool on; float cx, cy, lo, hi; };
 
@@ -350,8 +351,8 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     }
     int64_t size[2];
     scene_centered_translation(scene, n_lines, m->params.padding, m->shift, size);
-    if (size[0] <= 0 || size[0] > 65534 || size[1] != size[0])
-        return fail(FDCM_ERR_INVALID, "feature size out of the supported range (1..65534): " + std::to_string(size[0]));
+    if (size[0] <= 0 || size[0] > kMaxSide || size[1] != size[0])
+        return fail(FDCM_ERR_INVALID, "feature size out of the supported range (1.." + std::to_string(kMaxSide) + "): " + std::to_string(size[0]));
     m->keys = angle_keys(m->params.depth);
     const int D = (int)m->keys.size();
     MapDims dm;
@@ -364,14 +365,6 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     m->dm = dm;
     // every intermediate of the reference's first/second L2 pass is an exact integer iff 2*(side-1)^2 < 2^24
     m->exact = 2.0 * (double)(dm.W - 1) * (double)(dm.W - 1) < 16777216.0;
-    {
-        const char* e = std::getenv("FDCM_ROW_LITERAL");
-        m->row_literal = e && e[0] == '1';
-        const char* e2 = std::getenv("FDCM_ROW_MODE");   // A/B testing of the exact-regime row kernels
-        m->row_mode = m->row_literal ? 1 : (e2 ? std::atoi(e2) : 0);
-        const char* e3 = std::getenv("FDCM_FUSE_FILL");
-        m->fuse_fill = !(e3 && e3[0] == '0');
-    }
 
     // translated scene (core/math.h:352-354) and orientation bins with the host libm (dt3cpu.h:123-134)
     std::vector<float> ts((size_t)4 * n_lines);
@@ -430,12 +423,11 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     const size_t n_px = (size_t)D * dm.plane_elems;
     CUDA_TRY(m->planes.reserve(n_px * sizeof(float)));
     CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t)));
-    const bool band_ok = m->row_mode == 0 && dt_band_smem_bytes(dm) <= 200 * 1024;
-    const bool band_path = m->exact && m->params.distance != FDCM_L1 && band_ok;     // L2 / L2^2, exact regime
-    const bool band_l1 = m->params.distance == FDCM_L1 && band_ok;                    // L1, any size
+    if (dt_band_smem_bytes(dm) > 200 * 1024) return fail(FDCM_ERR_INVALID, "feature size too large for the band kernels");
+    const bool band_path = m->exact && m->params.distance != FDCM_L1;     // L2 / L2^2, exact regime
+    const bool band_l1 = m->params.distance == FDCM_L1;                   // L1, any size
     m->band_path = band_path;
     m->band_l1 = band_l1;
-    if (m->exact && !band_path && !band_l1) CUDA_TRY(m->g.reserve(n_px * sizeof(uint16_t)));
     if (band_path || band_l1) CUDA_TRY(m->band_info.reserve(dt_band_info_bytes(dm)));
     if (band_path) CUDA_TRY(m->band_spill.reserve(dt_band_spill_bytes(dm, m->col_hi - m->col_lo + 1)));
     if (m->params.distance != FDCM_L1 && !band_path) CUDA_TRY(m->stack.reserve(n_px * 8));
@@ -451,8 +443,7 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
 // second half of the host preparation, queued AFTER the build kernels so that its host work (length ordering of the
 // scene lines) overlaps the device build: keep the original scene resident for searches that pass scene == NULL
 static fdcm_status upload_build_scene(fdcm_dt3* m, const float* scene, int32_t n_lines, cudaStream_t s) {
-    if (n_lines == 0) return FDCM_OK;
-    std::lock_guard<std::mutex> lk(m->search_mutex);
+    if (n_lines == 0) return FDCM_OK;   // (the caller holds m->search_mutex)
     m->h_build_scene.assign(scene, scene + 4 * (size_t)n_lines);
     m->s_resident_is_build = true;
     return upload_search_scene(m, scene, n_lines, SceneFilter{false, 0, 0, 0, 0}, s);
@@ -478,7 +469,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
             launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, nullptr, 0, 0, s);
         }
-        fused_propagate = m->stage != 1 && m->fuse_fill && dt_fill_propagate_supported(dm);
+        fused_propagate = m->stage != 1 && dt_fill_propagate_supported(dm);
         if (fused_propagate) {
             KernelScope k("dt_l1_propagate", (double)dt_band_info_bytes(dm) + N, s);
             launch_dt_l1_propagate(m->band_info.p, m->planes.as<float>(), dm, m->prop, s);
@@ -495,7 +486,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
             launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, s);
         }
-        fused_propagate = m->stage != 1 && m->fuse_fill && dt_fill_propagate_supported(dm);
+        fused_propagate = m->stage != 1 && dt_fill_propagate_supported(dm);
         if (fused_propagate) {
             KernelScope k("dt_fill_propagate", N, s);
             launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, s);
@@ -503,43 +494,18 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             KernelScope k("dt_row_fill", N, s);
             launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
         }
-    } else if (m->exact) {
-        {
-            KernelScope k("dt_col_exact", N / 2, s);
-            launch_dt_col_exact(m->mask.as<uint32_t>(), dm, m->g.as<uint16_t>(), s);
-        }
-        if (dist == FDCM_L1) {
-            KernelScope k("dt_row_l1", N / 2 + N, s);
-            launch_dt_row_l1(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
-        } else if (m->row_mode == 1) {
-            KernelScope k("dt_row_literal", N / 2 + N, s);
-            launch_dt_pass_literal(true, true, m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->stack.p, s);
-        } else {
-            KernelScope k("dt_row_exact", N / 2 + N, s);
-            launch_dt_row_exact(m->g.as<uint16_t>(), m->planes.as<float>(), dm, m->col_lo, m->col_hi, s);
-        }
     } else {
+        // side > 2897, L2 / L2^2: float(q^2) rounds, the reference's float arithmetic is replayed literally
         {
             KernelScope k("mask_to_float", N, s);
             launch_mask_to_float(m->mask.as<uint32_t>(), dm, m->planes.as<float>(), s);
         }
-        if (dist == FDCM_L1) {
-            // L1 stays integer-exact at any size: build the u16 vertical distance on the fly
-            CUDA_TRY(m->g.reserve((size_t)dm.D * dm.plane_elems * sizeof(uint16_t)));
-            {
-                KernelScope k("dt_col_exact", N / 2, s);
-                launch_dt_col_exact(m->mask.as<uint32_t>(), dm, m->g.as<uint16_t>(), s);
-            }
-            KernelScope k("dt_row_l1", N / 2 + N, s);
-            launch_dt_row_l1(m->g.as<uint16_t>(), m->planes.as<float>(), dm, s);
-        } else {
-            {
-                KernelScope k("dt_col_literal", 2 * N, s);
-                launch_dt_pass_literal(false, false, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
-            }
-            KernelScope k("dt_row_literal", 2 * N, s);
-            launch_dt_pass_literal(false, true, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
+        {
+            KernelScope k("dt_col_literal", 2 * N, s);
+            launch_dt_pass_literal(false, false, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
         }
+        KernelScope k("dt_row_literal", 2 * N, s);
+        launch_dt_pass_literal(false, true, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
     }
     const bool need_sqrt = dist == FDCM_L2;
     if (m->stage == 1) {
@@ -599,15 +565,37 @@ extern "C" fdcm_status fdcm_dt3_build(const float* scene_xyxy, int32_t n_lines, 
     return FDCM_OK;
 }
 
+// A rebuild that fails half way (size check, allocation) must not leave a handle that mixes the old map with the new
+// scene: the map becomes the empty map (dt3cpu.h:180-181 state), which every entry point handles.
+static void invalidate_map(fdcm_dt3* m) {
+    m->n_lines = 0;
+    m->scene_bins.clear();
+    m->keys.clear();
+    m->dm = MapDims{0, 0, 0, 0, 0, 0};
+    m->shift[0] = m->shift[1] = 0.f;
+    m->s_scene_n = 0;
+    m->s_sorted_n = 0;
+    m->s_resident_is_build = false;
+    m->h_build_scene.clear();
+    m->last_n_hyp = 0;
+}
+
 static fdcm_status rebuild_impl(fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines, bool wait) {
     if (!m) return fail(FDCM_ERR_INVALID, "map is null");
     if (n_lines < 0 || (n_lines > 0 && !scene_xyxy)) return fail(FDCM_ERR_INVALID, "bad scene");
     CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t s;
     if (fdcm_status st = get_stream(m->device, &s)) return st;
+    std::lock_guard<std::mutex> lk(m->search_mutex);   // a search on this handle must not see a half-replaced map
     fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
     if (st == FDCM_OK) st = run_build_kernels(m, s);
     if (st == FDCM_OK) st = upload_build_scene(m, scene_xyxy, n_lines, s);
+    if (st != FDCM_OK) {
+        const std::string msg = g_last_error;
+        cudaStreamSynchronize(s);
+        invalidate_map(m);
+        g_last_error = msg;
+    }
     if (st == FDCM_OK && wait) {
         cudaError_t e = cudaStreamSynchronize(s);
         if (e != cudaSuccess) st = fail(FDCM_ERR_CUDA, std::string("rebuild: ") + cudaGetErrorString(e));
@@ -686,9 +674,12 @@ extern "C" fdcm_status fdcm_dt3_download_plane(const fdcm_dt3* m, int32_t plane,
     if (!m || !dst) return fail(FDCM_ERR_INVALID, "null argument");
     if (plane < 0 || plane >= m->dm.D) return fail(FDCM_ERR_INVALID, "plane out of range");
     CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;   // the stream the build kernels run on: a legacy-stream copy would not be ordered after an async rebuild
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
     const float* src = m->planes.as<float>() + (size_t)plane * m->dm.plane_elems;
-    CUDA_TRY(cudaMemcpy2D(dst, (size_t)m->dm.W * 4, src, (size_t)m->dm.pitch * 4, (size_t)m->dm.W * 4, m->dm.H,
-                          cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)m->dm.W * 4, src, (size_t)m->dm.pitch * 4, (size_t)m->dm.W * 4, m->dm.H,
+                               cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return FDCM_OK;
 }
 
@@ -696,9 +687,12 @@ extern "C" fdcm_status fdcm_dt3_download_mask(const fdcm_dt3* m, int32_t plane, 
     if (!m || !dst) return fail(FDCM_ERR_INVALID, "null argument");
     if (plane < 0 || plane >= m->dm.D) return fail(FDCM_ERR_INVALID, "plane out of range");
     CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
     std::vector<uint32_t> w((size_t)m->dm.H * m->dm.wwords);
-    CUDA_TRY(cudaMemcpy(w.data(), m->mask.as<uint32_t>() + (size_t)plane * m->dm.H * m->dm.wwords, w.size() * 4,
-                        cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpyAsync(w.data(), m->mask.as<uint32_t>() + (size_t)plane * m->dm.H * m->dm.wwords, w.size() * 4,
+                             cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     for (int y = 0; y < m->dm.H; ++y)
         for (int x = 0; x < m->dm.W; ++x)
             dst[(size_t)y * m->dm.W + x] = (w[(size_t)y * m->dm.wwords + (x >> 5)] >> (x & 31)) & 1u;
@@ -1055,7 +1049,11 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     m->last_n_hyp = 0;
     m->last_stats = fdcm_search_stats{0, 0, 0, 0};
     // defaultmatch.cpp:40-41
-    const bool resident_scene = scene == nullptr;
+    // n_scene == FDCM_SCENE_RESIDENT: the scene the map was built from (already on the device); an EMPTY scene
+    // (n_scene == 0, whatever the pointer) yields no matches like the reference (defaultmatch.cpp:40)
+    const bool resident_scene = n_scene == FDCM_SCENE_RESIDENT;
+    if (n_scene < 0 && !resident_scene) return fail(FDCM_ERR_INVALID, "bad scene size");
+    if (n_scene > 0 && !scene) return fail(FDCM_ERR_INVALID, "scene is null");
     if (resident_scene) {
         scene = m->h_build_scene.data();
         n_scene = (int32_t)(m->h_build_scene.size() / 4);
@@ -1153,8 +1151,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     so.counters = m->s_counters.as<unsigned long long>();
     sl.perm = nullptr;
     sl.hyp_ready = nullptr;
-    static const bool no_order = [] { const char* e = std::getenv("FDCM_SEARCH_UNORDERED"); return e && e[0] == '1'; }();
-    if (!no_order && H >= 4096 && H < (int64_t)1 << 31) {
+    if (H >= 4096 && H < (int64_t)1 << 31) {
         // process the hypotheses in the spatial order of their scene lines (L2 locality of the map gathers)
         const float ex = m->s_scene_max[0] - m->s_scene_min[0], ey = m->s_scene_max[1] - m->s_scene_min[1];
         const int cells_x = std::min(4096, std::max(1, (int)(ex / 128.f) + 1));
@@ -1332,7 +1329,10 @@ extern "C" fdcm_status fdcm_search_last_hypotheses(const fdcm_dt3* m, int32_t* o
     if (m->last_n_hyp == 0) return FDCM_OK;
     if (capacity < m->last_n_hyp || !out) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
     CUDA_TRY(cudaSetDevice(m->device));
-    CUDA_TRY(cudaMemcpy(out, m->s_hyp.p, (size_t)m->last_n_hyp * 16, cudaMemcpyDeviceToHost));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    CUDA_TRY(cudaMemcpyAsync(out, m->s_hyp.p, (size_t)m->last_n_hyp * 16, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
     return FDCM_OK;
 }
 
@@ -1400,7 +1400,7 @@ extern "C" fdcm_status fdcm_concentric_search(const float* tmpl, int32_t L, cons
 }
 
 extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows, int32_t n, int32_t literal, int32_t device, float* out) {
-    if (!g_rows || !out || n_rows <= 0 || n <= 0 || n > 4000) return fail(FDCM_ERR_INVALID, "bad argument");
+    if (!g_rows || !out || n_rows <= 0 || n <= 0 || n > 4000 || (literal != 1 && literal != 2)) return fail(FDCM_ERR_INVALID, "bad argument");
     CUDA_TRY(cudaSetDevice(device));
     cudaStream_t s;
     if (fdcm_status st = get_stream(device, &s)) return st;
@@ -1415,13 +1415,13 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
     if (e == cudaSuccess) e = cudaMemsetAsync(dg.p, 0xFF, dm.plane_elems * 2, s);
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(dg.p, (size_t)dm.pitch * 2, g_rows, (size_t)n * 2, (size_t)n * 2, n_rows, cudaMemcpyHostToDevice, s);
     if (e == cudaSuccess) {
-        KernelScope k(literal == 2 ? "dt_row_band" : (literal ? "dt_row_literal" : "dt_row_exact"), 0.0, s);
+        KernelScope k(literal == 2 ? "dt_row_band" : "dt_row_literal", 0.0, s);
         if (literal == 2) {
             launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, 0, dm.H - 1, s);
             launch_dt_row_fill(dp.as<float>(), dm, ds.p, 0, dm.W - 1, s);
+        } else {
+            launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
         }
-        else if (literal) launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
-        else launch_dt_row_exact(dg.as<uint16_t>(), dp.as<float>(), dm, 0, dm.W - 1, s);
     }
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpy2DAsync(out, (size_t)n * 4, dp.p, (size_t)dm.pitch * 4, (size_t)n * 4, n_rows, cudaMemcpyDeviceToHost, s);

@@ -7,12 +7,9 @@ namespace fdcm {
 
 // ---- dt3_kernels.cu ----
 void launch_raster(const float* d_lines, const int32_t* d_bins, int n_lines, const MapDims& dm, uint32_t* d_mask, cudaStream_t s);
-void launch_dt_col_exact(const uint32_t* d_mask, const MapDims& dm, uint16_t* d_g, cudaStream_t s);
 void launch_mask_to_float(const uint32_t* d_mask, const MapDims& dm, float* d_planes, cudaStream_t s);
 void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, float* d_planes, const MapDims& dm,
                             void* d_stack, cudaStream_t s);
-void launch_dt_row_exact(const uint16_t* d_g, float* d_planes, const MapDims& dm, int col_lo, int col_hi, cudaStream_t s);
-void launch_dt_row_l1(const uint16_t* d_g, float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, bool sqrt_first, cudaStream_t s);
 void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, int32_t* d_rtab, cudaStream_t s);

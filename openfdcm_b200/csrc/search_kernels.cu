@@ -1,6 +1,6 @@
 // search_kernels.cu — hot path 2: template search kernels (sm_100a).
 //
-// One thread per alignment hypothesis fuses the reference's
+// One warp per alignment hypothesis fuses the reference's
 //   establishSearchStrategy<DefaultSearch>   (matching/src/searchstrategies/defaultsearch.cpp:29-49)
 //   align / transform                        (core/math.h:387-406, 341-344)
 //   optimize<BatchOptimize|DefaultOptimize>  (matching/src/optimizestrategies/batchoptimize.cpp:15-99)
@@ -88,20 +88,6 @@ __device__ __forceinline__ float eigen_sum_lazy(int n, CostFn c) {
     return r;
 }
 
-// one line term of evaluate<Dt3Cpu> (dt3cpu.cpp:158-174): |P_bin(p1) - P_bin(p2)| with truncating casts
-__device__ __forceinline__ float line_cost(const MapView& m, const Rigid& T, const float4 p, int bin, float offx, float offy) {
-    float ax, ay, bx, by;
-    xform(T, p.x, p.y, ax, ay);
-    xform(T, p.z, p.w, bx, by);
-    int x1 = (int)(ax + offx), y1 = (int)(ay + offy), x2 = (int)(bx + offx), y2 = (int)(by + offy);
-    x1 = min(max(x1, 0), m.dm.W - 1); x2 = min(max(x2, 0), m.dm.W - 1);   // no-ops inside the bounds of
-    y1 = min(max(y1, 0), m.dm.H - 1); y2 = min(max(y2, 0), m.dm.H - 1);   // minmaxTranslation; guard only
-    const float* P = m.planes + (size_t)bin * m.dm.plane_elems;
-    const float v1 = __ldg(P + (size_t)y1 * m.dm.pitch + x1);
-    const float v2 = __ldg(P + (size_t)y2 * m.dm.pitch + x2);
-    return fabsf(v1 - v2);
-}
-
 // minmaxTranslation (dt3cpu.cpp:30-75) given the bbox of the aligned template already shifted by the
 // scene translation
 __device__ void minmax_dev(float mnx, float mny, float mxx, float mxy, float sizex, float sizey, float vx, float vy,
@@ -138,149 +124,6 @@ __device__ void minmax_dev(float mnx, float mny, float mxx, float mxy, float siz
 
 // (long) conversion of the reference (batchoptimize.cpp:51): truncation toward zero
 __device__ __forceinline__ long long trunc_ll(float x) { return (long long)x; }
-
-// =============================================================================================
-// K5+K6: one hypothesis per thread
-// =============================================================================================
-__global__ void __launch_bounds__(128) search_kernel(const __grid_constant__ MapView map,
-                                                     const __grid_constant__ SlopeTableDev table,
-                                                     const __grid_constant__ TemplatesView tv,
-                                                     const __grid_constant__ SceneView sv,
-                                                     const __grid_constant__ SearchLaunch sl,
-                                                     const __grid_constant__ SearchOutputs out) {
-    extern __shared__ uint8_t s_bins[];   // [line][thread] orientation plane of each aligned template line
-    const int tid = threadIdx.x;
-    const int nthr = blockDim.x;
-    const long long h = (long long)blockIdx.x * nthr + tid;
-    const bool active = h < sl.n_hyp;
-    unsigned long long n_eval = 0, n_look = 0;
-    bool valid = false;
-
-    if (active) {
-        // ---- hypothesis index -> (template, template-line rank, scene window slot, reversed) ----
-        int lo = 0, hi = tv.n_tmpl;   // largest t with hyp_off[t] <= h
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (sl.hyp_off[mid] <= h) lo = mid; else hi = mid;
-        }
-        const int t = lo;
-        const int loc = (int)(h - sl.hyp_off[t]);
-        const int l0 = tv.offsets[t];
-        const int L = tv.offsets[t + 1] - l0;
-        const int nS = min(sv.n, sl.max_scene_lines);
-        const int rank = loc / (2 * nS);
-        const int slot = (loc >> 1) % nS;
-        const int rev = loc & 1;
-        const int tline = tv.argsort[l0 + rank];
-        // closest scene length: binarySearch with std::greater (core/math.h:138-146)
-        const float value = tv.line_len[l0 + tline];
-        int b0 = 0, b1 = sv.n;   // lower_bound: first i with !(sorted_len[i] > value)
-        while (b0 < b1) {
-            const int mid = (b0 + b1) >> 1;
-            if (sv.sorted_len[mid] > value) b0 = mid + 1; else b1 = mid;
-        }
-        int closest;
-        if (b0 == 0) closest = 0;
-        else if (b0 == sv.n) closest = sv.n - 1;
-        else closest = fabsf(value - sv.sorted_len[b0]) < fabsf(value - sv.sorted_len[b0 - 1]) ? b0 : b0 - 1;
-        // getCenteredRange (searchstrategies/defaultsearch.h:40-47)
-        int rb = max(0, closest - sl.max_scene_lines / 2);
-        const int re = min(rb + sl.max_scene_lines, sv.n);
-        rb = max(0, re - sl.max_scene_lines);
-        const int sline = sv.sorted_idx[rb + slot];
-        out.hyp[h] = make_int4(t + sl.tmpl_idx_base, tline, sline, rev);
-
-        // ---- alignment (defaultmatch.cpp:57-69) ----
-        const float4* TL = tv.lines + l0;
-        float avx, avy;
-        const Rigid T = align_dev(TL[tline], sv.lines[sline], rev, avx, avy);
-
-        // ---- BatchOptimize::func (batchoptimize.cpp:15-99) ----
-        // relativelyEqual(|ax|+|ay|, 0) (core/math.h:183-189)
-        const float asum = fabsf(avx) + fabsf(avy);
-        const bool null_vec = (double)asum <= (double)FLT_EPSILON + 1e-10 * (double)asum;
-        if (!null_vec) {
-            float svx, svy;
-            rasterize_vector_dev(avx, avy, svx, svy);
-            // bbox of the aligned template + orientation plane per line (dt3cpu.cpp:144-148)
-            float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-            for (int i = 0; i < L; ++i) {
-                const float4 p = __ldg(TL + i);
-                float ax, ay, bx, by;
-                xform(T, p.x, p.y, ax, ay);
-                xform(T, p.z, p.w, bx, by);
-                mnx = fminf(mnx, fminf(ax, bx)); mxx = fmaxf(mxx, fmaxf(ax, bx));
-                mny = fminf(mny, fminf(ay, by)); mxy = fmaxf(mxy, fmaxf(ay, by));
-                s_bins[i * nthr + tid] = (uint8_t)bin_of_slope_dev(table, (by - ay) / (bx - ax));
-            }
-            float min_mul, max_mul;
-            minmax_dev(mnx + map.shift_x, mny + map.shift_y, mxx + map.shift_x, mxy + map.shift_y, (float)map.dm.W,
-                       (float)map.dm.H, svx, svy, min_mul, max_mul);
-            if (isfinite(min_mul) && isfinite(max_mul)) {
-                auto score_at = [&](float trx, float try_) -> float {
-                    const float offx = map.shift_x + trx, offy = map.shift_y + try_;   // dt3cpu.cpp:153
-                    ++n_eval;
-                    return eigen_sum_lazy(L, [&](int i) {
-                        return line_cost(map, T, __ldg(TL + i), s_bins[i * nthr + tid], offx, offy);
-                    });
-                };
-                float back = score_at(0.f, 0.f);         // scores.back()
-                float best = back, best_tx = 0.f, best_ty = 0.f;
-                const long long B = sl.batch;
-                const long long maxm = trunc_ll(max_mul), minm = trunc_ll(min_mul);
-                for (long long k = 1; k <= maxm; k += B) {
-                    float bmin = 0.f, blast = 0.f;
-                    long long barg = k;
-                    for (long long j = k; j < k + B && j <= maxm; ++j) {
-                        const float s = score_at((float)j * svx, (float)j * svy);
-                        if (j == k || s < bmin) { bmin = s; barg = j; }   // std::min_element: first minimum
-                        blast = s;
-                    }
-                    if (bmin > back) break;
-                    back = bmin;
-                    if (bmin < best) { best = bmin; best_tx = (float)barg * svx; best_ty = (float)barg * svy; }
-                    if (bmin < blast) break;
-                }
-                for (long long k = -1; k >= minm; k -= B) {
-                    float bmin = 0.f, blast = 0.f;
-                    long long barg = k;
-                    for (long long j = k; j > k - B && j >= minm; --j) {
-                        const float s = score_at((float)j * svx, (float)j * svy);
-                        if (j == k || s < bmin) { bmin = s; barg = j; }
-                        blast = s;
-                    }
-                    if (bmin > back) break;
-                    back = bmin;
-                    if (bmin < best) { best = bmin; best_tx = (float)barg * svx; best_ty = (float)barg * svy; }
-                    if (bmin < blast) break;
-                }
-                n_look = n_eval * 2ull * (unsigned long long)L;
-                // Match{tmplIdx, score, combine(translation, T)} (defaultmatch.cpp:82-84, core/math.h:427-432)
-                fdcm_match m;
-                m.tmpl_idx = t + sl.tmpl_idx_base;
-                m.score = tv.denom ? best / tv.denom[t] : best;
-                m.transform[0] = T.r00; m.transform[1] = T.r01; m.transform[2] = T.tx + best_tx;
-                m.transform[3] = T.r10; m.transform[4] = T.r11; m.transform[5] = T.ty + best_ty;
-                out.rec[h] = m;
-                valid = true;
-            }
-        }
-        out.valid[h] = valid ? 1 : 0;
-    }
-    // counters
-    unsigned long long nv = valid ? 1ull : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        n_eval += __shfl_down_sync(0xffffffffu, n_eval, o);
-        n_look += __shfl_down_sync(0xffffffffu, n_look, o);
-        nv += __shfl_down_sync(0xffffffffu, nv, o);
-    }
-    if ((tid & 31) == 0) {
-        atomicAdd(out.counters + 0, n_eval);
-        atomicAdd(out.counters + 1, n_look);
-        atomicAdd(out.counters + 2, nv);
-    }
-}
 
 // hypothesis index -> (template, template line, scene line, reversed): establishSearchStrategy<DefaultSearch>
 // (defaultsearch.cpp:29-49) evaluated for one combination
@@ -348,216 +191,6 @@ void launch_search_order(const TemplatesView& tv, const SceneView& sv, const Sea
                          int key_bits, int4* d_hyp, cudaStream_t s) {
     search_key_kernel<<<(unsigned)((sl.n_hyp + 255) / 256), 256, 0, s>>>(tv, sv, sl, minx, miny, cells_x, d_keys, d_idx, d_hyp);
     cub::DeviceRadixSort::SortPairs(d_temp, temp_bytes, d_keys, d_keys_out, d_idx, d_perm, (int)sl.n_hyp, 0, key_bits, s);
-}
-
-// =============================================================================================
-// K5+K6, cooperative version: 8 lanes per hypothesis.  Eigen's packet-4, 2x-unrolled reduction keeps 8
-// partial sums (A0..A3, B0..B3) where partial k accumulates lines k, k+8, k+16, ... in order; lane k of a
-// group carries exactly that partial sum, so the reference's summation order is preserved while the 8 lanes
-// share one hypothesis.  All candidates of a batch (up to kChunk at a time) are scored concurrently: per
-// template line a lane transforms the end points once and issues 2*kChunk independent gathers.
-// =============================================================================================
-constexpr int kGroup = 8;
-constexpr int kChunk = 10;
-
-__global__ void __launch_bounds__(128) search8_kernel(const __grid_constant__ MapView map,
-                                                      const __grid_constant__ SlopeTableDev table,
-                                                      const __grid_constant__ TemplatesView tv,
-                                                      const __grid_constant__ SceneView sv,
-                                                      const __grid_constant__ SearchLaunch sl,
-                                                      const __grid_constant__ SearchOutputs out) {
-    extern __shared__ uint8_t s_bins[];   // [line][hypothesis of the block]
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int k = tid & (kGroup - 1);                    // lane within the group = Eigen partial-sum index
-    const int gbase = lane & ~(kGroup - 1);              // first lane of the group inside the warp
-    const unsigned gmask = 0xFFu << gbase;
-    const int hyps_per_block = blockDim.x / kGroup;
-    const int hb = tid / kGroup;                         // hypothesis slot in the block
-    const long long slot_idx = (long long)blockIdx.x * hyps_per_block + hb;
-    const bool active = slot_idx < sl.n_hyp;
-    const long long h = active ? (sl.perm ? (long long)sl.perm[slot_idx] : slot_idx) : 0;
-    unsigned long long n_eval = 0, n_look = 0;
-    bool valid = false;
-
-    if (active) {
-        int t, l0, L;
-        float avx, avy;
-        Rigid T;
-        if (sl.direct_align) {
-            // optimize<BatchOptimize>(templates, alignments, featuremap) (batchoptimize.cpp:6-123): template h as given
-            t = (int)h;
-            l0 = tv.offsets[t];
-            L = tv.offsets[t + 1] - l0;
-            T = Rigid{1.f, 0.f, 0.f, 0.f, 1.f, 0.f};      // x*1 + y*0 + 0 is exact: coordinates pass through unchanged
-            avx = sl.direct_align[h].x;
-            avy = sl.direct_align[h].y;
-        } else {
-            const HypDecode d = decode_hypothesis(h, tv, sv, sl);
-            t = d.t; l0 = d.l0; L = d.L;
-            if (k == 0) out.hyp[h] = make_int4(t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);
-            T = align_dev(tv.lines[l0 + d.tline], sv.lines[d.sline], d.rev, avx, avy);   // defaultmatch.cpp:57-69
-        }
-        const float4* TL = tv.lines + l0;
-        const float asum = fabsf(avx) + fabsf(avy);
-        const bool null_vec = (double)asum <= (double)FLT_EPSILON + 1e-10 * (double)asum;   // batchoptimize.cpp:20
-        if (!null_vec) {
-            float svx, svy;
-            rasterize_vector_dev(avx, avy, svx, svy);
-            // bbox of the aligned template + orientation plane of every line (lane k takes lines k, k+8, ...)
-            float mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
-            for (int i = k; i < L; i += kGroup) {
-                const float4 p = __ldg(TL + i);
-                float ax, ay, bx, by;
-                xform(T, p.x, p.y, ax, ay);
-                xform(T, p.z, p.w, bx, by);
-                mnx = fminf(mnx, fminf(ax, bx)); mxx = fmaxf(mxx, fmaxf(ax, bx));
-                mny = fminf(mny, fminf(ay, by)); mxy = fmaxf(mxy, fmaxf(ay, by));
-                s_bins[i * hyps_per_block + hb] = (uint8_t)bin_of_slope_dev(table, (by - ay) / (bx - ax));
-            }
-#pragma unroll
-            for (int o = 1; o < kGroup; o <<= 1) {
-                mnx = fminf(mnx, __shfl_xor_sync(gmask, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(gmask, mxx, o));
-                mny = fminf(mny, __shfl_xor_sync(gmask, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(gmask, mxy, o));
-            }
-            __syncwarp(gmask);   // bins of the tail lines are read by other lanes of the group
-            float min_mul, max_mul;
-            minmax_dev(mnx + map.shift_x, mny + map.shift_y, mxx + map.shift_x, mxy + map.shift_y, (float)map.dm.W,
-                       (float)map.dm.H, svx, svy, min_mul, max_mul);
-            if (isfinite(min_mul) && isfinite(max_mul)) {
-                const int n4 = L & ~3, n8 = L & ~7;
-                // the (at most two) extra lines of this lane: packet line and tail line (Redux.h order)
-                const int pk_line = (k < 4) ? ((n8 > 0) ? ((n4 > n8) ? n8 + k : -1) : ((n4 == 4) ? k : -1)) : -1;
-                const int tl_line = (k < L - n4 && k < 3) ? n4 + k : -1;
-                const float* planes = map.planes;
-                const unsigned pitch = (unsigned)map.dm.pitch;
-                const int Wm1 = map.dm.W - 1, Hm1 = map.dm.H - 1;
-
-                // scores of nc <= kChunk translations j0, j0+dj, ... (multipliers of (svx, svy)); result on all lanes
-                auto score_chunk = [&](long long j0, int dj, int nc, float* sc) {
-                    float offx[kChunk], offy[kChunk], acc[kChunk], pk[kChunk], tl[kChunk];
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) {
-                        const float m = (float)(j0 + (long long)j * dj);
-                        offx[j] = map.shift_x + m * svx;     // dt3cpu.cpp:153: sceneTranslation + translation
-                        offy[j] = map.shift_y + m * svy;
-                        acc[j] = 0.f; pk[j] = 0.f; tl[j] = 0.f;
-                    }
-                    auto line_costs = [&](int i, float* dst, bool accumulate) {
-                        const float4 p = __ldg(TL + i);
-                        float ax, ay, bx, by;
-                        xform(T, p.x, p.y, ax, ay);
-                        xform(T, p.z, p.w, bx, by);
-                        const float* P = planes + (size_t)s_bins[i * hyps_per_block + hb] * map.dm.plane_elems;
-                        float c[kChunk];
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j) {
-                            if (j < nc) {
-                                int x1 = (int)(ax + offx[j]), y1 = (int)(ay + offy[j]);
-                                int x2 = (int)(bx + offx[j]), y2 = (int)(by + offy[j]);
-                                x1 = min(max(x1, 0), Wm1); x2 = min(max(x2, 0), Wm1);   // guards only (no-ops inside
-                                y1 = min(max(y1, 0), Hm1); y2 = min(max(y2, 0), Hm1);   // the minmaxTranslation bounds)
-                                c[j] = fabsf(__ldg(P + ((unsigned)y1 * pitch + (unsigned)x1)) -
-                                             __ldg(P + ((unsigned)y2 * pitch + (unsigned)x2)));
-                            } else {
-                                c[j] = 0.f;
-                            }
-                        }
-#pragma unroll
-                        for (int j = 0; j < kChunk; ++j) dst[j] = accumulate ? dst[j] + c[j] : c[j];
-                    };
-                    bool first = true;
-                    for (int i = k; i < n8; i += kGroup) {
-                        line_costs(i, acc, !first);
-                        first = false;
-                    }
-                    if (pk_line >= 0) line_costs(pk_line, pk, false);
-                    if (tl_line >= 0) line_costs(tl_line, tl, false);
-#pragma unroll
-                    for (int j = 0; j < kChunk; ++j) {
-                        float r;
-                        if (L >= 4) {
-                            float A;
-                            if (n8 > 0) {
-                                A = acc[j] + __shfl_down_sync(gmask, acc[j], 4, kGroup);            // A += B
-                                if (n4 > n8) A = A + pk[j];                                          // A += c[n8..n8+3]
-                            } else {
-                                A = pk[j];                                                           // single packet
-                            }
-                            const float t02 = A + __shfl_down_sync(gmask, A, 2, kGroup);            // (A0+A2), (A1+A3)
-                            r = t02 + __shfl_down_sync(gmask, t02, 1, kGroup);                      // predux
-                            for (int q = 0; q < L - n4; ++q) r = r + __shfl_sync(gmask, tl[j], q, kGroup);   // scalar tail
-                        } else {
-                            r = __shfl_sync(gmask, tl[j], 0, kGroup);
-                            for (int q = 1; q < L; ++q) r = r + __shfl_sync(gmask, tl[j], q, kGroup);
-                        }
-                        sc[j] = __shfl_sync(gmask, r, 0, kGroup);
-                    }
-                    n_eval += nc;
-                };
-
-                float sc[kChunk];
-                score_chunk(0, 0, 1, sc);
-                float back = sc[0];                       // scores.back()
-                float best = back, best_tx = 0.f, best_ty = 0.f;
-                const long long B = sl.batch;
-                const long long maxm = trunc_ll(max_mul), minm = trunc_ll(min_mul);
-                for (int dir = 1; dir >= -1; dir -= 2) {
-                    // batchoptimize.cpp:51-71 (dir = +1) and :74-94 (dir = -1)
-                    const long long lim = dir > 0 ? maxm : -minm;     // multipliers run 1..lim in units of dir
-                    for (long long kk = 1; kk <= lim; kk += B) {
-                        const long long jend = min(kk + B - 1, lim);
-                        float bmin = 0.f, blast = 0.f;
-                        long long barg = kk;
-                        for (long long c0 = kk; c0 <= jend; c0 += kChunk) {
-                            const int nc = (int)min((long long)kChunk, jend - c0 + 1);
-                            score_chunk(dir * c0, dir, nc, sc);
-#pragma unroll
-                            for (int j = 0; j < kChunk; ++j) {
-                                if (j < nc) {
-                                    if ((c0 == kk && j == 0) || sc[j] < bmin) { bmin = sc[j]; barg = c0 + j; }   // first minimum
-                                    blast = sc[j];
-                                }
-                            }
-                        }
-                        if (bmin > back) break;
-                        back = bmin;
-                        if (bmin < best) {
-                            best = bmin;
-                            best_tx = (float)(dir * barg) * svx;
-                            best_ty = (float)(dir * barg) * svy;
-                        }
-                        if (bmin < blast) break;
-                    }
-                }
-                valid = true;
-                if (k == 0) {
-                    n_look = n_eval * 2ull * (unsigned long long)L;
-                    fdcm_match m;   // Match{tmplIdx, score, combine(translation, T)} (defaultmatch.cpp:82-84)
-                    m.tmpl_idx = t + sl.tmpl_idx_base;
-                    m.score = tv.denom ? best / tv.denom[t] : best;
-                    m.transform[0] = T.r00; m.transform[1] = T.r01; m.transform[2] = T.tx + best_tx;
-                    m.transform[3] = T.r10; m.transform[4] = T.r11; m.transform[5] = T.ty + best_ty;
-                    out.rec[h] = m;
-                }
-            }
-        }
-        if (k == 0) out.valid[h] = valid ? 1 : 0;
-    }
-    // counters (one contribution per hypothesis: lane 0 of each group)
-    unsigned long long ne = (active && k == 0) ? n_eval : 0ull, nl = (active && k == 0) ? n_look : 0ull;
-    unsigned long long nv = (active && k == 0 && valid) ? 1ull : 0ull;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ne += __shfl_down_sync(0xffffffffu, ne, o);
-        nl += __shfl_down_sync(0xffffffffu, nl, o);
-        nv += __shfl_down_sync(0xffffffffu, nv, o);
-    }
-    if (lane == 0) {
-        atomicAdd(out.counters + 0, ne);
-        atomicAdd(out.counters + 1, nl);
-        atomicAdd(out.counters + 2, nv);
-    }
 }
 
 // =============================================================================================
@@ -754,25 +387,6 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
 void launch_search(const MapView& map, const SlopeTableDev& table, const TemplatesView& tv, const SceneView& sv,
                    const SearchLaunch& sl, const SearchOutputs& out, cudaStream_t s) {
     if (sl.n_hyp <= 0) return;
-    static const bool use_v1 = [] { const char* e = getenv("FDCM_SEARCH_V1"); return e && e[0] == '1'; }();
-    if (use_v1 && !sl.direct_align) {   // one hypothesis per thread (kept for A/B measurements)
-        int threads = 128;
-        while (threads > 32 && (size_t)threads * tv.max_lines > 96 * 1024) threads >>= 1;
-        const size_t smem = (size_t)threads * tv.max_lines;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const unsigned grid = (unsigned)((sl.n_hyp + threads - 1) / threads);
-        search_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
-        return;
-    }
-    static const bool use_v2 = [] { const char* e = getenv("FDCM_SEARCH_V2"); return e && e[0] == '1'; }();
-    if (use_v2) {                       // 8 lanes per hypothesis (kept for A/B measurements)
-        const int threads = 128, hyps = threads / kGroup;
-        const size_t smem = (size_t)hyps * tv.max_lines;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(search8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        const unsigned grid = (unsigned)((sl.n_hyp + hyps - 1) / hyps);
-        search8_kernel<<<grid, threads, smem, s>>>(map, table, tv, sv, sl, out);
-        return;
-    }
     const int threads = 128, hyps = threads / 32;
     const size_t smem = (size_t)hyps * ((size_t)tv.max_lines * 16 + (((size_t)tv.max_lines + 15) & ~(size_t)15));
     if (smem > 48 * 1024) cudaFuncSetAttribute(search_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in include/fdcm_b200.h but not exported"
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
     assert sorted(_lib.SIGNATURES) == declared
-    assert lib.fdcm_abi_version() == 2
+    assert lib.fdcm_abi_version() == 3
 
 
 def test_struct_layouts_match_header():

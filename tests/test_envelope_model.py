@@ -193,3 +193,78 @@ def test_first_minimum_by_bit_pattern_order():
         bits = s.view(np.uint32)
         kmin = bits.min()
         assert int(np.flatnonzero(bits == kmin)[0]) == barg and np.float32(bmin).view(np.uint32) == kmin
+
+
+# ---- per-band candidate pruning (round 2): every band prunes its own columns -------------------------------------
+class RingStack(Stack):
+    """Loose stack that only remembers its last `cap` entries: older ones fall off the bottom and are kept as survivors
+    (they can no longer be popped); when every remembered entry has been popped the stack is treated as empty, i.e. the
+    next vertex starts at pixel 0.  Both deviations only ever keep MORE vertices than the unbounded loose stack."""
+
+    def __init__(self, cap):
+        super().__init__(loose=True)
+        self.cap, self.fallen = cap, set()
+
+    def column(self, v, g, wm1):
+        super().column(v, g, wm1)
+        while len(self.e) > self.cap:
+            self.fallen.add(self.e.pop(0)[1])
+
+    def survivors(self):
+        return self.fallen | {e[1] for e in self.e}
+
+
+def _vertical_distance(mask, y):
+    """g(v) of row y: distance to the nearest edge pixel of column v (BIG: none), what the band records encode"""
+    h, w = mask.shape
+    g = np.full(w, BIG, np.int64)
+    for v in range(w):
+        ys = np.flatnonzero(mask[:, v])
+        if ys.size:
+            g[v] = np.abs(ys - y).min()
+    return g
+
+
+def band_candidates(mask, r0, band, seg, cap):
+    """Columns a band [r0, r0 + band) has to visit: columns with an edge pixel inside the band, plus the survivors of
+    loose stack passes over the band's first and last row, run independently on column segments of width `seg` (no
+    join: a vertex of the row's envelope is also a vertex of the envelope of its own segment)."""
+    h, w = mask.shape
+    r1 = min(r0 + band, h) - 1
+    cand = set(np.flatnonzero(mask[r0:r1 + 1].any(0)).tolist())
+    for y in (r0, r1):
+        g = _vertical_distance(mask, y)
+        for s0 in range(0, w, seg):
+            st = RingStack(cap)
+            for v in range(s0, min(s0 + seg, w)):
+                if g[v] != BIG:
+                    st.column(v, int(g[v]), w - 1)
+            cand |= st.survivors()
+    return cand
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_per_band_candidates_cover_every_row_of_the_band(seed):
+    """An edge pixel above (below) a band that owns a pixel of one of its rows is strictly nearest on the open segment
+    towards that pixel, which crosses the band's first (last) row: it survives a loose pass over that row."""
+    rng = np.random.default_rng(500 + seed)
+    w, h = int(rng.integers(20, 100)), int(rng.integers(20, 70))
+    band, seg, cap = int(rng.choice([4, 8, 16])), int(rng.choice([5, 9, 16, 33])), int(rng.choice([1, 2, 4, 8]))
+    mask = np.zeros((h, w), bool)
+    for _ in range(int(rng.integers(1, 9))):
+        x0, y0 = int(rng.integers(0, w)), int(rng.integers(0, h))
+        dx, dy = int(rng.integers(-25, 26)), int(rng.integers(-12, 13))
+        for t in np.linspace(0, 1, 40):
+            x, y = int(round(x0 + t * dx)), int(round(y0 + t * dy))
+            if 0 <= x < w and 0 <= y < h:
+                mask[y, x] = True
+    if seed % 3 == 0:
+        mask[int(rng.integers(0, h)), :] = True                     # a full horizontal line: every column is a vertex
+    for r0 in range(0, h, band):
+        cand = band_candidates(mask, r0, band, seg, cap)
+        for y in range(r0, min(r0 + band, h)):
+            g = _vertical_distance(mask, y)
+            assert _owners(g) <= cand, (seed, r0, y)
+            gp = np.where(np.isin(np.arange(w), list(cand)), g, BIG)
+            xs = int(rng.integers(0, w + 1))
+            assert np.array_equal(fill(joined_envelope(gp, xs), w), literal(g)), (seed, r0, y)

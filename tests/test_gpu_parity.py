@@ -246,7 +246,6 @@ def test_row_pass_exact_kernel_vs_literal_oracle(n):
             r = np.repeat(r[:: 8], 8)[:n] if n >= 8 else r      # plateaus
         rows.append(r)
     g = np.stack([np.asarray(r).astype(np.int64)[:n] for r in rows]).astype(np.uint16)
-    got = _dt_rows(g, literal=0)
     lit = _dt_rows(g, literal=1)
     band = _dt_rows(g, literal=2)   # lane-per-row band kernel (the product path), g given explicitly
     fmax = np.finfo(np.float32).max
@@ -254,7 +253,6 @@ def test_row_pass_exact_kernel_vs_literal_oracle(n):
         f = np.where(g[i] == big, fmax, g[i].astype(np.float64) ** 2).astype(F32)
         want = orc.dt_pass_l2_1d(f)
         assert np.array_equal(lit[i], want), f"literal kernel row {i}"
-        assert np.array_equal(got[i], want), f"exact kernel row {i}: first diff at {np.flatnonzero(got[i] != want)[:5]}"
         assert np.array_equal(band[i], want), f"band kernel row {i}: first diff at {np.flatnonzero(band[i] != want)[:5]}"
 
 
@@ -453,3 +451,45 @@ def test_randomised_scenes_bit_exact(case):
     assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
     assert np.array_equal(got["score"], want["score"], equal_nan=True)
     assert np.array_equal(got["transform"], want["transform"], equal_nan=True)
+
+
+def test_empty_search_scene_yields_no_matches():
+    """defaultmatch.cpp:40: an empty originalScene gives no matches — it must NOT fall back to the resident build scene
+    (that is what n_scene == FDCM_SCENE_RESIDENT / scene=None asks for explicitly)."""
+    scene, tmpls = _workload(8, n_tmpl=3)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    s, o = fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10)
+    assert fdcm.search(fdcm.DefaultMatch(), s, o, g, tmpls, np.zeros((4, 0), F32)) == []
+    assert len(fdcm.search_all(g, tmpls, np.zeros((4, 0), F32), s, o)) == 0
+    assert len(fdcm.search_all(g, tmpls, None, s, o)) == len(fdcm.search_all(g, tmpls, scene, s, o)) > 0
+
+
+def test_failed_rebuild_leaves_an_empty_map():
+    """A rebuild that is rejected (feature size out of range) must not leave a handle mixing the old map with the new
+    scene: the map becomes the empty map and a search on it returns nothing."""
+    scene, tmpls = _workload(8, n_tmpl=3)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    huge = (scene * 100.0).astype(F32)           # side ~ 96000 > the supported maximum
+    with pytest.raises(fdcm.FdcmError):
+        g.rebuild(huge)
+    g._refresh()
+    assert g.get_feature_size().tolist() == [0, 0] and g.depth == 0
+    assert len(fdcm.search_all(g, tmpls, None, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10))) == 0
+    g.rebuild(scene)                              # and the handle is still usable
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    assert np.array_equal(g.plane(3), c.plane(3))
+
+
+def test_two_devices_in_one_process():
+    """The opt-in shared-memory attributes are per device: maps built on two devices from one process."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two devices")
+    scene, tmpls = _workload(8, n_tmpl=3)
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    want = c.search(tmpls, scene, 4, 4, batch=10)
+    for dev in (0, 1, 0):
+        g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5, device=dev))
+        assert np.array_equal(g.plane(11), c.plane(11))
+        got = fdcm.search_all(g, fdcm.TemplateSet(tmpls, device=dev), scene, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10))
+        assert np.array_equal(got["score"], want["score"])
