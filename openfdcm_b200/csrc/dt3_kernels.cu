@@ -6,7 +6,7 @@
 //      dt_pass_literal_kernel   Felzenszwalb lower-envelope pass, literal incl. the in-place aliasing
 //      dt_row_l1_kernel         L1 second pass
 //   K3 propagate_kernel         propagateOrientation: 4*D circular min-plus steps, D values in registers
-//   K4 integral_kernel          lineIntegral: sequential fp32 running sums along each plane's discrete lines
+//   K4 integral_tma.cu          lineIntegral: sequential fp32 running sums along each plane's discrete lines
 // Layout: orientation-major [D][H][pitch] fp32, pitch % 32 == 0.
 // All float arithmetic is non-fused (-fmad=false) and ordered exactly as the reference's expressions.
 #include <cstdlib>
@@ -249,311 +249,6 @@ __global__ void __launch_bounds__(128) propagate_generic_kernel(float* __restric
 }
 
 // =============================================================================================
-// K4: lineIntegral (core/imgproc.h:38-84).  A plane's discrete direction (rx, ry) has one unit
-// component.  x-major: column i adds column i-1 shifted by dy_i = R(i) - R(i-1), R(j) =
-// (long)roundf(j*ry), so pixel (x_i, c + R(i)) continues the chain of pixel (x_{i-1}, c + R(i-1)):
-// one thread per chain c carries the strictly sequential fp32 running sum (((a0+a1)+a2)+...).
-// y-major is the same with rows/columns swapped (and is the coalesced case for a [H][W] plane).
-// =============================================================================================
-// R(i) = (long)roundf(float(i) * r) per plane (r = ry for x-major, rx for y-major planes): the cumulative
-// minor-axis shift of a chain after i major-axis steps (sum of the reference's per-step deltas, imgproc.h:55,72)
-__global__ void integral_shift_table_kernel(int32_t* __restrict__ rtab, int len, const __grid_constant__ IntegralParams ip) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = blockIdx.y;
-    if (i >= len) return;
-    const float r = ip.mode[d] == 1 ? ip.ry[d] : ip.rx[d];
-    rtab[(size_t)d * len + i] = (int32_t)round_to_ll((float)i * r);
-}
-
-__device__ __forceinline__ void cp_async_f32(uint32_t smem_addr, const float* gptr) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-// y-major planes: thread per chain, the row access of a warp is one coalesced 128-byte segment; kYU loads in
-// flight per thread hide the HBM latency (the running sum itself is the only serial dependency).
-constexpr int kYU = 32;
-constexpr int kYPrefetch = 96;          // rows of L2 prefetch distance
-
-__global__ void __launch_bounds__(128) integral_ymajor_kernel(float* __restrict__ planes, MapDims dm,
-                                                              const __grid_constant__ IntegralParams ip,
-                                                              const int32_t* __restrict__ rtab, int rlen) {
-    const int d = blockIdx.y;
-    if (ip.mode[d] != 2) return;
-    const int32_t* R = rtab + (size_t)d * rlen;
-    const float ry = ip.ry[d];
-    const int Rend = R[dm.H - 1];
-    const int cmin = Rend > 0 ? -Rend : 0;
-    const int cmax = (Rend < 0 ? -Rend : 0) + dm.W - 1;
-    int c = cmin + blockIdx.x * blockDim.x + threadIdx.x;
-    if (cmin + (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u)) > cmax) return;   // whole warp past the last chain
-    if (c > cmax) c = 0x20000000;                                                         // idle lane: every x is out of range
-    // rows are visited at y = p0y + i*sy: fold the direction into a row pointer and a signed pitch
-    const long long rstep = ry < 0 ? -(long long)dm.pitch : (long long)dm.pitch;
-    float* row = planes + (size_t)d * dm.plane_elems + (ry < 0 ? (size_t)(dm.H - 1) * dm.pitch : 0);
-    float acc = 0.f;
-    bool have = false;
-    const int lane = threadIdx.x & 31;
-    const int cw = cmin + (int)(blockIdx.x * blockDim.x + (threadIdx.x & ~31u));   // first chain of the warp
-    for (int i0 = 0; i0 < dm.H; i0 += kYU) {
-        float a[kYU];
-        const int32_t rl = (i0 + lane < dm.H) ? __ldg(R + i0 + lane) : 0x40000000;   // lane k: shift of row i0+k
-        {   // pull the rows kYPrefetch ahead into L2: lane k takes row i0 + kYPrefetch + k (the warp's 128-byte segment
-            // of that row starts at chain cw; it may straddle two lines)
-            const int ip = i0 + kYPrefetch + lane;
-            if (ip < dm.H) {
-                const int xp = cw + __ldg(R + ip);
-                const float* rowp = row + (long long)(kYPrefetch + lane) * rstep;
-                if ((unsigned)xp < (unsigned)dm.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + xp));
-                if ((unsigned)(xp + 31) < (unsigned)dm.W) asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + xp + 31));
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < kYU; ++k) {
-            const int x = c + __shfl_sync(0xffffffffu, rl, k);
-            a[k] = ((unsigned)x < (unsigned)dm.W) ? row[(long long)k * rstep + x] : 0.f;
-        }
-#pragma unroll
-        for (int k = 0; k < kYU; ++k) {
-            const int x = c + __shfl_sync(0xffffffffu, rl, k);
-            if ((unsigned)x < (unsigned)dm.W) {
-                if (have) { acc = a[k] + acc; row[(long long)k * rstep + x] = acc; }
-                else { acc = a[k]; have = true; }
-            } else {
-                have = false;
-            }
-        }
-        row += (long long)kYU * rstep;
-    }
-}
-
-// x-major planes: a warp owns 32 consecutive chains and walks the columns in blocks of 32.  Each block is
-// staged through a shared-memory tile (<= 64 rows x 32 columns, row segments loaded / stored as coalesced
-// 128-byte pieces), lane j then runs chain j sequentially across the 32 columns of the tile.  Tiles are double
-// buffered with cp.async: the next tile's rows are in flight while the current one is summed and written back.
-constexpr int kTileRows = 64, kTilePitch = 33;
-
-struct XTile {              // geometry of one 32-column block for one warp
-    int ybase, r_lo, r_hi, off, ncols;
-};
-
-__global__ void __launch_bounds__(128) integral_xmajor_scalar_kernel(float* __restrict__ planes, MapDims dm,
-                                                              const __grid_constant__ IntegralParams ip,
-                                                              const int32_t* __restrict__ rtab, int rlen) {
-    extern __shared__ __align__(16) float tiles_all[];       // [4 warps][2 buffers][kTileRows * kTilePitch]
-    const int d = blockIdx.y;
-    if (ip.mode[d] != 1) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile0 = tiles_all + (size_t)warp * 2 * kTileRows * kTilePitch;
-    const uint32_t tile0_s = (uint32_t)__cvta_generic_to_shared(tile0);
-    float* P = planes + (size_t)d * dm.plane_elems;
-    const int32_t* R = rtab + (size_t)d * rlen;
-    const float rx = ip.rx[d];
-    const int sx = rx < 0 ? -1 : 1;
-    const int p0x = rx < 0 ? dm.W - 1 : 0;
-    const int Rend = R[dm.W - 1];
-    const int cmin = Rend > 0 ? -Rend : 0;
-    const int cmax = (Rend < 0 ? -Rend : 0) + dm.H - 1;
-    const int c0 = cmin + (blockIdx.x * 4 + warp) * 32;                    // first chain of this warp
-    if (c0 > cmax) return;
-    auto geometry = [&](int i0) {
-        XTile g;
-        const int i = i0 + lane;                                           // this lane's column step (load/store role)
-        const bool col_ok = i < dm.W;
-        const int Rl = R[col_ok ? i : dm.W - 1];
-        const int Ra = __shfl_sync(0xffffffffu, Rl, 0);
-        const int Rb = __shfl_sync(0xffffffffu, Rl, min(31, dm.W - 1 - i0));
-        const int Rmin = min(Ra, Rb);
-        g.ybase = c0 + Rmin;
-        const int nrows = 32 + abs(Ra - Rb);
-        g.r_lo = max(0, -g.ybase);                                         // rows of the tile inside the image
-        g.r_hi = min(nrows, dm.H - g.ybase);
-        g.off = col_ok ? Rl - Rmin : 0x40000000;                           // tile row of chain c0 in this lane's column
-        g.ncols = min(32, dm.W - i0);
-        return g;
-    };
-    // row r of the tile, lane = column; the element belongs to chain (r - off)
-    auto load = [&](int i0, int buf) {
-        if (i0 < dm.W) {
-            const XTile g = geometry(i0);
-            const float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (p0x + (i0 + lane) * sx);
-            uint32_t sp = tile0_s + (uint32_t)((buf * kTileRows + g.r_lo) * kTilePitch + lane) * 4u;
-            for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch, sp += kTilePitch * 4u)
-                if ((unsigned)(r - g.off) < 32u) cp_async_f32(sp, gp);
-        }
-        cp_async_commit();
-    };
-    float acc = 0.f;
-    bool have = false;
-    load(0, 0);
-    int buf = 0;
-    for (int i0 = 0; i0 < dm.W; i0 += 32, buf ^= 1) {
-        load(i0 + 32, buf ^ 1);
-        cp_async_wait<1>();
-        __syncwarp();
-        float* tile = tile0 + (size_t)buf * kTileRows * kTilePitch;
-        const XTile g = geometry(i0);
-        // ---- sequential sums: lane = chain; the 32 tile values of the chain go through registers ----
-        float v[32];
-        int rr[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const int r = lane + __shfl_sync(0xffffffffu, g.off, j);       // tile row of this lane's chain in column j
-            rr[j] = (j < g.ncols && r >= g.r_lo && r < g.r_hi) ? r * kTilePitch + j : -1;
-            v[j] = rr[j] >= 0 ? tile[rr[j]] : 0.f;
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            if (rr[j] >= 0) {
-                if (have) { acc = v[j] + acc; tile[rr[j]] = acc; }
-                else { acc = v[j]; have = true; }
-            } else if (j < g.ncols) {
-                have = false;
-            }
-        }
-        __syncwarp();
-        // ---- store ----
-        float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (p0x + (i0 + lane) * sx);
-        for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch)
-            if ((unsigned)(r - g.off) < 32u) *gp = tile[r * kTilePitch + lane];
-        __syncwarp();
-    }
-}
-
-// x-major planes, vector path (W % 4 == 0): the same tiles, but staged with 16-byte cp.async (LDGSTS.128 moves 512
-// bytes per warp instruction; the 4-byte form is limited to about one element per cycle per SM) as full row segments
-// in memory order (pitch kVecPitch floats, 16-byte aligned rows).  A column walk over 16-byte staged rows can only
-// reach the 8 banks congruent to the column (mod 4), so the four 8-lane groups of the warp run 0..3 columns behind
-// each other: bank = 4*(lane%8) + 4*shift + column - lane/8 is then distinct for all 32 lanes.
-constexpr int kVecPitch = 36;
-constexpr int kSkew = 3;
-
-__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const float* gptr) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
-}
-
-__global__ void __launch_bounds__(128) integral_xmajor_kernel(float* __restrict__ planes, MapDims dm,
-                                                              const __grid_constant__ IntegralParams ip,
-                                                              const int32_t* __restrict__ rtab, int rlen) {
-    extern __shared__ __align__(16) float tiles_all[];       // [4 warps][2 buffers][kTileRows * kVecPitch]
-    const int d = blockIdx.y;
-    if (ip.mode[d] != 1) return;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* tile0 = tiles_all + (size_t)warp * 2 * kTileRows * kVecPitch;
-    const uint32_t tile0_s = (uint32_t)__cvta_generic_to_shared(tile0);
-    float* P = planes + (size_t)d * dm.plane_elems;
-    const int32_t* R = rtab + (size_t)d * rlen;
-    const bool fwd = !(ip.rx[d] < 0);                                      // column step i is x = i (fwd) or x = W-1-i
-    const int Rend = R[dm.W - 1];
-    const int cmin = Rend > 0 ? -Rend : 0;
-    const int cmax = (Rend < 0 ? -Rend : 0) + dm.H - 1;
-    const int c0 = cmin + (blockIdx.x * 4 + warp) * 32;                    // first chain of this warp
-    if (c0 > cmax) return;
-    const int grp = lane >> 3;                                             // this lane's lag in the column walk
-    auto geometry = [&](int i0) {
-        XTile g;
-        const int i = i0 + lane;                                           // this lane's column step (shift-table role)
-        const bool col_ok = i < dm.W;
-        const int Rl = R[col_ok ? i : dm.W - 1];
-        const int Ra = __shfl_sync(0xffffffffu, Rl, 0);
-        const int Rb = __shfl_sync(0xffffffffu, Rl, min(31, dm.W - 1 - i0));
-        const int Rmin = min(Ra, Rb);
-        g.ybase = c0 + Rmin;
-        const int nrows = 32 + abs(Ra - Rb);
-        g.r_lo = max(0, -g.ybase);                                         // rows of the tile inside the image
-        g.r_hi = min(nrows, dm.H - g.ybase);
-        g.off = col_ok ? Rl - Rmin : 0x40000000;                           // tile row of chain c0 at this lane's column step
-        g.ncols = min(32, dm.W - i0);
-        return g;
-    };
-    // memory column m of the tile <-> x = xbase + m; column step j sits at m = j (fwd) or 31 - j
-    auto load = [&](int i0, int buf) {
-        if (i0 < dm.W) {
-            const XTile g = geometry(i0);
-            const int xbase = fwd ? i0 : dm.W - 32 - i0;
-            const int x = xbase + 4 * (lane & 7);
-            const bool chunk_ok = x >= 0 && x + 3 < dm.W;
-            const int r0 = g.r_lo + (lane >> 3);
-            const float* gp = P + (long long)(g.ybase + r0) * dm.pitch + x;
-            uint32_t sp = tile0_s + (uint32_t)((buf * kTileRows + r0) * kVecPitch + 4 * (lane & 7)) * 4u;
-            for (int r = r0; r < g.r_hi; r += 4, gp += 4 * (long long)dm.pitch, sp += 4u * kVecPitch * 4u)
-                if (chunk_ok) cp_async_16(sp, gp);
-        }
-        cp_async_commit();
-    };
-    float acc = 0.f;
-    bool have = false;
-    load(0, 0);
-    int buf = 0;
-    for (int i0 = 0; i0 < dm.W; i0 += 32, buf ^= 1) {
-        load(i0 + 32, buf ^ 1);
-        cp_async_wait<1>();
-        __syncwarp();
-        float* tile = tile0 + (size_t)buf * kTileRows * kVecPitch;
-        const XTile g = geometry(i0);
-        // ---- sequential sums: lane = chain, step s handles column step j = s - grp ----
-        const int mb = fwd ? 0 : 31, ms = fwd ? 1 : -1;                   // memory column of column step j: mb + ms * j
-        const bool interior = g.ncols == 32 && g.r_lo == 0 && g.ybase + 64 <= dm.H;   // every chain element of the tile exists
-        if (interior && __all_sync(0xffffffffu, have)) {
-            float v[32 + kSkew];
-            int rr[32 + kSkew];
-#pragma unroll
-            for (int s = 0; s < 32 + kSkew; ++s) {
-                const int j = s - grp;
-                if (s >= kSkew && s < 32) {                                // all four groups are inside the tile
-                    rr[s] = (lane + __shfl_sync(0xffffffffu, g.off, j)) * kVecPitch + mb + ms * j;
-                    v[s] = tile[rr[s]];
-                } else {
-                    rr[s] = (lane + __shfl_sync(0xffffffffu, g.off, j & 31)) * kVecPitch + mb + ms * j;
-                    v[s] = (unsigned)j < 32u ? tile[rr[s]] : 0.f;
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < 32 + kSkew; ++s) {
-                if (s >= kSkew && s < 32) {
-                    acc = v[s] + acc;
-                    tile[rr[s]] = acc;
-                } else if ((unsigned)(s - grp) < 32u) {
-                    acc = v[s] + acc;
-                    tile[rr[s]] = acc;
-                }
-            }
-        } else {
-            float v[32 + kSkew];
-            int rr[32 + kSkew];
-#pragma unroll
-            for (int s = 0; s < 32 + kSkew; ++s) {
-                const int j = s - grp;
-                const int r = lane + __shfl_sync(0xffffffffu, g.off, j & 31);  // tile row of this lane's chain at column step j
-                const bool ok = (unsigned)j < (unsigned)g.ncols && r >= g.r_lo && r < g.r_hi;
-                rr[s] = ok ? r * kVecPitch + mb + ms * j : ((unsigned)j < (unsigned)g.ncols ? -1 : -2);
-                v[s] = ok ? tile[rr[s]] : 0.f;
-            }
-#pragma unroll
-            for (int s = 0; s < 32 + kSkew; ++s) {
-                if (rr[s] >= 0) {
-                    if (have) { acc = v[s] + acc; tile[rr[s]] = acc; }
-                    else { acc = v[s]; have = true; }
-                } else if (rr[s] == -1) {                                  // a column step of the image outside the plane
-                    have = false;
-                }
-            }
-        }
-        __syncwarp();
-        // ---- store: row r of the tile, lane = memory column; the element belongs to chain (r - off) ----
-        const int j_of_lane = fwd ? lane : 31 - lane;
-        const int off_m = __shfl_sync(0xffffffffu, g.off, j_of_lane);
-        const int xbase = fwd ? i0 : dm.W - 32 - i0;
-        float* gp = P + (long long)(g.ybase + g.r_lo) * dm.pitch + (xbase + lane);
-        for (int r = g.r_lo; r < g.r_hi; ++r, gp += dm.pitch)
-            if ((unsigned)(r - off_m) < 32u) *gp = tile[r * kVecPitch + lane];
-        __syncwarp();
-    }
-}
-
-// =============================================================================================
 // launchers
 // =============================================================================================
 static inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
@@ -594,33 +289,6 @@ void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, 
         case 30: propagate_kernel<30><<<grid, 128, 0, s>>>(d_planes, dm, pp, sqrt_first ? 1 : 0); break;
         case 4: propagate_kernel<4><<<grid, 128, 0, s>>>(d_planes, dm, pp, sqrt_first ? 1 : 0); break;
         default: propagate_generic_kernel<<<grid, 128, 0, s>>>(d_planes, dm, pp, sqrt_first ? 1 : 0); break;
-    }
-}
-
-void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, int32_t* d_rtab, cudaStream_t s) {
-    const int rlen = dm.W > dm.H ? dm.W : dm.H;
-    {
-        dim3 tgrid(cdiv(rlen, 256), dm.D);
-        integral_shift_table_kernel<<<tgrid, 256, 0, s>>>(d_rtab, rlen, ip);
-    }
-    dim3 grid(cdiv((size_t)dm.W + dm.H, 128), dm.D);   // #chains <= W + H
-    bool any_x = false, any_y = false;
-    for (int d = 0; d < dm.D; ++d) {
-        any_x |= ip.mode[d] == 1;
-        any_y |= ip.mode[d] == 2;
-    }
-    if (any_y) integral_ymajor_kernel<<<grid, 128, 0, s>>>(d_planes, dm, ip, d_rtab, rlen);
-    if (any_x) {
-        // (per call: the attribute is per device and a process may drive several devices)
-        if (dm.W % 4 == 0) {
-            const size_t smem = (size_t)4 * 2 * kTileRows * kVecPitch * sizeof(float);
-            cudaFuncSetAttribute(integral_xmajor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            integral_xmajor_kernel<<<grid, 128, smem, s>>>(d_planes, dm, ip, d_rtab, rlen);
-        } else {   // widths that are no multiple of 4 floats: the 4-byte staging variant
-            const size_t smem = (size_t)4 * 2 * kTileRows * kTilePitch * sizeof(float);
-            cudaFuncSetAttribute(integral_xmajor_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            integral_xmajor_scalar_kernel<<<grid, 128, smem, s>>>(d_planes, dm, ip, d_rtab, rlen);
-        }
     }
 }
 

@@ -218,7 +218,13 @@ struct fdcm_dt3 {
     SlopeTableDev table_dev{};
     PropParams prop{};
     IntegralParams integ{};
-    DevBuf planes, mask, stack, lines, bins, rtab, band_info, band_spill;
+    DevBuf planes, mask, stack, lines, bins, rtab, band_info, band_spill, integ_items;
+    // lineIntegral plan (shift table, work items, tensor maps): a function of the map geometry and the planes pointer
+    IntegralPlanDev integ_plan{};
+    int plan_W = -1, plan_H = -1, plan_D = -1, plan_pitch = -1;
+    const void* plan_planes = nullptr;
+    int plan_tables_depth = -1;
+    int n_sms = 148;
     bool band_path = false, band_l1 = false;   // which distance-transform formulation this map uses (set by prepare)
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
@@ -243,7 +249,7 @@ struct fdcm_dt3 {
 
     ~fdcm_dt3() {
         cudaSetDevice(device);
-        for (DevBuf* b : {&planes, &mask, &stack, &lines, &bins, &rtab, &band_info, &band_spill, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
+        for (DevBuf* b : {&planes, &mask, &stack, &lines, &bins, &rtab, &band_info, &band_spill, &integ_items, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
                           &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n, &s_keys, &s_keys2, &s_idx,
                           &s_perm, &s_sort_tmp})
             b->release();
@@ -336,6 +342,92 @@ static fdcm_status upload_search_scene(const fdcm_dt3* m, const float* scene, in
 
 static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s);
 
+// ---- TMA tensor maps: cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda) ----
+namespace fdcm {
+bool encode_planes_map(CUtensorMap* out, const void* planes, int W, int H, int D, int pitch, int bx, int by, int bz) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeFn)p;
+    }();
+    if (!fn) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * 4 * (cuuint64_t)H};
+    const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bz};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(planes), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}   // namespace fdcm
+
+// lineIntegral plan: R(i) = (long)roundf(float(i) * r) (imgproc.h:55,72; same IEEE operations as the reference, on the
+// host), the (plane, strip) work items in decreasing order of work, and the tensor maps of the planes.
+static fdcm_status build_integral_plan(fdcm_dt3* m, cudaStream_t s) {
+    const MapDims& dm = m->dm;
+    const bool same = m->plan_W == dm.W && m->plan_H == dm.H && m->plan_D == dm.D && m->plan_pitch == dm.pitch &&
+                      m->plan_planes == m->planes.p && m->plan_tables_depth == m->tables_depth;
+    if (same) return FDCM_OK;
+    m->plan_W = -1;
+    const int rlen = std::max(dm.W, dm.H);
+    std::vector<int32_t> rtab((size_t)dm.D * rlen);
+    struct Item { double work; int2 it; };
+    std::vector<Item> items;
+    const int CW = integral_strip_chains();
+    for (int d = 0; d < dm.D; ++d) {
+        const int mode = m->integ.mode[d];
+        const float r = mode == 1 ? m->integ.ry[d] : m->integ.rx[d];
+        int32_t* R = rtab.data() + (size_t)d * rlen;
+        for (int i = 0; i < rlen; ++i) R[i] = (int32_t)(long long)std::round((float)i * r);
+        if (mode != 1 && mode != 2) continue;
+        const int n_major = mode == 1 ? dm.W : dm.H, n_minor = mode == 1 ? dm.H : dm.W;
+        const int Rend = R[n_major - 1];
+        const int cmin = Rend > 0 ? -Rend : 0, cmax = (Rend < 0 ? -Rend : 0) + n_minor - 1;
+        for (int c0 = cmin; c0 <= cmax; c0 += CW) {
+            // steps at which the middle chain of the strip lies inside the image (R is monotone): the strip's work
+            const int cm = std::min(c0 + CW / 2, cmax);
+            int lo = 0, hi = n_major;   // count i with 0 <= cm + R(i) < n_minor
+            int cnt = 0;
+            if (Rend == 0) cnt = (cm >= 0 && cm < n_minor) ? n_major : 0;
+            else {
+                auto first_ge = [&](int v) {   // first i with sgn * R(i) >= v for the monotone direction
+                    int a = lo, b = hi;
+                    while (a < b) { const int mid = (a + b) / 2; if ((Rend > 0 ? R[mid] : -R[mid]) >= v) b = mid; else a = mid + 1; }
+                    return a;
+                };
+                if (Rend > 0) cnt = first_ge(n_minor - cm) - first_ge(-cm);          // -cm <= R < n_minor - cm
+                else cnt = first_ge(cm + 1) - first_ge(cm - n_minor + 1);            // cm - n_minor < -R <= cm
+            }
+            items.push_back(Item{(double)std::max(cnt, 1), make_int2(d, c0)});
+        }
+    }
+    std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.work > b.work; });
+    std::vector<int2> flat(items.size());
+    for (size_t i = 0; i < items.size(); ++i) flat[i] = items[i].it;
+    CUDA_TRY(m->rtab.reserve(rtab.size() * sizeof(int32_t)));
+    CUDA_TRY(m->integ_items.reserve(std::max<size_t>(8, flat.size() * sizeof(int2))));
+    CUDA_TRY(cudaMemcpyAsync(m->rtab.p, rtab.data(), rtab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(m->integ_items.p, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaStreamSynchronize(s));   // the host vectors go out of scope (rare: only when the geometry changes)
+    IntegralPlanDev& pl = m->integ_plan;
+    pl.rtab = m->rtab.as<int32_t>();
+    pl.rlen = rlen;
+    pl.items = m->integ_items.as<int2>();
+    pl.n_items = (int)flat.size();
+    if (!integral_tma_encode(m->planes.p, dm, &pl.map_y, &pl.map_x))
+        return fail(FDCM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature-map planes");
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device) == cudaSuccess && sms > 0) m->n_sms = sms;
+    m->plan_W = dm.W; m->plan_H = dm.H; m->plan_D = dm.D; m->plan_pitch = dm.pitch;
+    m->plan_planes = m->planes.p;
+    m->plan_tables_depth = m->tables_depth;
+    return FDCM_OK;
+}
+
 // host preparation: shift, size, keys, bins (reference dt3cpu.h:180-193), then upload
 static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n_lines, cudaStream_t s) {
     m->n_lines = n_lines;
@@ -422,7 +514,7 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     // device allocations (grow-only)
     const size_t n_px = (size_t)D * dm.plane_elems;
     CUDA_TRY(m->planes.reserve(n_px * sizeof(float)));
-    CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t)));
+    CUDA_TRY(m->mask.reserve((size_t)D * dm.H * dm.wwords * sizeof(uint32_t) + 256));   // + the work counters of the build kernels
     if (dt_band_smem_bytes(dm) > 200 * 1024) return fail(FDCM_ERR_INVALID, "feature size too large for the band kernels");
     const bool band_path = m->exact && m->params.distance != FDCM_L1;     // L2 / L2^2, exact regime
     const bool band_l1 = m->params.distance == FDCM_L1;                   // L1, any size
@@ -431,13 +523,12 @@ static fdcm_status prepare_and_upload(fdcm_dt3* m, const float* scene, int32_t n
     if (band_path || band_l1) CUDA_TRY(m->band_info.reserve(dt_band_info_bytes(dm)));
     if (band_path) CUDA_TRY(m->band_spill.reserve(dt_band_spill_bytes(dm, m->col_hi - m->col_lo + 1)));
     if (m->params.distance != FDCM_L1 && !band_path) CUDA_TRY(m->stack.reserve(n_px * 8));
-    CUDA_TRY(m->rtab.reserve((size_t)D * std::max(dm.W, dm.H) * sizeof(int32_t)));
     CUDA_TRY(m->lines.reserve((size_t)n_lines * 16));
     CUDA_TRY(m->bins.reserve((size_t)n_lines * 4));
     CUDA_TRY(cudaMemcpyAsync(m->lines.p, ts.data(), (size_t)n_lines * 16, cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaMemcpyAsync(m->bins.p, m->scene_bins.data(), (size_t)n_lines * 4, cudaMemcpyHostToDevice, s));
     // (copies from pageable memory return once the source has been staged: ts may go out of scope)
-    return FDCM_OK;
+    return build_integral_plan(m, s);
 }
 
 // second half of the host preparation, queued AFTER the build kernels so that its host work (length ordering of the
@@ -456,7 +547,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
     const size_t mask_bytes = (size_t)dm.D * dm.H * dm.wwords * sizeof(uint32_t);
     {
         KernelScope k("mask_clear", (double)mask_bytes, s, 0);   // cudaMemsetAsync, not one of our kernels
-        CUDA_TRY(cudaMemsetAsync(m->mask.p, 0, mask_bytes, s));
+        CUDA_TRY(cudaMemsetAsync(m->mask.p, 0, mask_bytes + 256, s));   // (+ the work counters behind the mask)
     }
     {
         KernelScope k("raster", 0.0, s);
@@ -519,8 +610,10 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             launch_propagate(m->planes.as<float>(), dm, m->prop, need_sqrt, s);
         }
         if (m->stage == 0) {
-            KernelScope k("integral", 2 * N, s, 3);
-            launch_integral(m->planes.as<float>(), dm, m->integ, m->rtab.as<int32_t>(), s);
+            KernelScope k("integral", 2 * N, s, 1);
+            IntegralPlanDev pl = m->integ_plan;
+            pl.counter = reinterpret_cast<int*>(m->mask.as<unsigned char>() + mask_bytes);
+            launch_integral_tma(m->planes.as<float>(), dm, m->integ, pl, m->n_sms, s);
         }
     }
     CUDA_TRY(cudaGetLastError());

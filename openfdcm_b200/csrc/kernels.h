@@ -1,5 +1,7 @@
 // kernels.h — launcher declarations shared by the C-ABI layer (fdcm_api.cu)
 #pragma once
+#include <cuda.h>   // CUtensorMap (types only: the driver entry point is resolved at run time)
+
 #include "common.cuh"
 #include "../../include/fdcm_b200.h"
 
@@ -12,7 +14,21 @@ void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, f
                             void* d_stack, cudaStream_t s);
 void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, bool sqrt_first, cudaStream_t s);
-void launch_integral(float* d_planes, const MapDims& dm, const IntegralParams& ip, int32_t* d_rtab, cudaStream_t s);
+
+// ---- integral_tma.cu: lineIntegral as one persistent TMA-fed kernel ----
+struct IntegralPlanDev {
+    const int32_t* rtab;         // [D][rlen] cumulative minor-axis shift R(i) = (long)roundf(i * r) per plane
+    int rlen;
+    const int2* items;           // (plane, first chain of the strip), heaviest first
+    int n_items;
+    int* counter;                // work counter, zero before the launch
+    CUtensorMap map_y, map_x;    // the planes with the y-major / x-major box shapes
+};
+size_t integral_tma_smem_bytes();
+int integral_strip_chains();
+bool integral_tma_encode(const void* planes, const MapDims& dm, CUtensorMap* map_y, CUtensorMap* map_x);
+void launch_integral_tma(float* d_planes, const MapDims& dm, const IntegralParams& ip, const IntegralPlanDev& plan, int n_sms,
+                         cudaStream_t s);
 
 // ---- dt_band_kernels.cu (exact regime, lane-per-row formulation) ----
 int dt_band_count(const MapDims& dm);
