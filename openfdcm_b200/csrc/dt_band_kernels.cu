@@ -17,6 +17,7 @@
 // branches), the top of the stack in registers, the next 32 entries in a shared-memory ring, older ones spilled to a
 // per-row global array.  The pixel fill walks the envelope once per row and goes through a 32x32 shared-memory
 // transposition so that global stores are 128-byte row segments.
+#include <algorithm>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -30,10 +31,8 @@ constexpr uint32_t kNone16 = 0xFFFFu;
 // per (plane, band, column): {edge bits of the 32 rows, (rows from the band's first row up to the last edge above) |
 // (rows from the band's last row down to the first edge below) << 16}; 0xFFFF = no such edge
 // =============================================================================================
-// row_range (optional): per plane {-(first row holding an edge), last row holding an edge}, both by atomicMax on a buffer
-// preset to a very negative value
 __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __restrict__ mask, MapDims dm,
-                                                          uint2* __restrict__ info, int nbands, int32_t* __restrict__ row_range) {
+                                                          uint2* __restrict__ info, int nbands) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* M = reinterpret_cast<uint32_t*>(smem_raw);                       // [nbands][64] column bit words
     uint16_t* up16 = reinterpret_cast<uint16_t*>(M + (size_t)nbands * 64);     // [nbands][64]
@@ -73,13 +72,6 @@ __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __rest
             if (m) {
                 if (last < 0) first = b * 32 + __ffs(m) - 1;
                 last = b * 32 + 31 - __clz(m);
-            }
-        }
-        if (row_range) {
-            const int nf = __reduce_max_sync(0xffffffffu, -first), nl = __reduce_max_sync(0xffffffffu, last);
-            if ((threadIdx.x & 31) == 0 && nl >= 0) {
-                atomicMax(row_range + 2 * d, nf);
-                atomicMax(row_range + 2 * d + 1, nl);
             }
         }
         int next = -1;
@@ -239,9 +231,8 @@ struct RowMeta {
 // chain per row is half as long as with one stack and twice as many warps are in flight.
 // Workspace rows are padded to 32 per band (row id = (d * nbands + b) * 32 + lane) so that the rows past H of the last
 // band need no special case: they build an envelope nobody reads.
-// kCand: candidate pass for one row (row `rsel` of the band, lane 0 only, loose pops).  cand: 1 bit per column, columns
-// whose bit is clear are skipped (far bands).
-template <bool kFromG, bool kRev, bool kCand>
+// cand (shared memory, may be null): 1 bit per column, columns whose bit is clear are skipped.
+template <bool kFromG, bool kRev>
 __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restrict__ info_row, const uint16_t* __restrict__ g,
                                               const uint16_t* __restrict__ g_row, const MapDims& dm, int d, int row0, int x_begin,
                                               int x_end, int lane, int rsel, const uint32_t* __restrict__ cand) {
@@ -254,12 +245,12 @@ __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restr
     uint2 e_next = kNone;
     if (!kFromG && nchunks > 0 && chunk_x0(0) + lane < W) e_next = info_row[chunk_x0(0)];
     uint32_t cw_next = 0xFFFFFFFFu;
-    if (cand && nchunks > 0) cw_next = __ldcg(cand + (chunk_x0(0) >> 5));
+    if (cand && nchunks > 0) cw_next = cand[chunk_x0(0) >> 5];
     for (int c = 0; c < nchunks; ++c) {
         const int x0 = chunk_x0(c);
         const uint2 e = e_next;
         const uint32_t cw = cw_next;
-        if (cand && c + 1 < nchunks) cw_next = __ldcg(cand + (chunk_x0(c + 1) >> 5));
+        if (cand && c + 1 < nchunks) cw_next = cand[chunk_x0(c + 1) >> 5];
         unsigned todo;
         if (kFromG) {
             // lane = column here: which of the 32 columns hold a finite value in ANY row of the band
@@ -292,84 +283,101 @@ __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restr
                 const int da = __ffs(below) - 1 - 31, db = (int)(ud >> 16);       // (row of the first edge at or below) - 31
                 gv = min(rsel + (above ? ua : ub), l31 + (below ? da : db));
             }
-            if (kCand) fin = lane == 0;
             if (fin) {
-                if (kRev) st.template column_rev<kCand>(x0 + j, gv, Wm1);
-                else st.template column<kCand>(x0 + j, gv, Wm1);
+                if (kRev) st.column_rev(x0 + j, gv, Wm1);
+                else st.column(x0 + j, gv, Wm1);
             }
         }
     }
 }
 
-// Candidate pruning for far bands.  Let r_top / r_bot be the first / last row of a plane that holds an edge pixel.  For a
-// row y above r_top every site is the top-most edge pixel of its column, and if column v owns an (integer) pixel P of row
-// y, then on the whole open segment from P to that site the site is the STRICTLY nearest one; the segment crosses row
-// y0 = r_top - 1, so v has an interval of positive length on the continuous lower envelope of row y0.  Hence the columns
-// that survive a stack pass over row y0 which only pops vertices that are nowhere strictly minimal (kLoose) are a
-// superset of the owners of every row above; the same holds below r_bot with y0 = r_bot + 1.  The first 2*D CTAs of the
-// grid run that pass (one (plane, side) each, left / right halves by the two warps, lane 0 only) and publish a
-// column bit mask; bands that lie entirely above r_top or below r_bot wait for it and skip all other columns.
-struct BandAux {
-    int32_t* row_range;     // [D][2]  {-(first edge row), last edge row}; very negative when the plane has no edge
-    int32_t* flags;         // [D][2]  set when the candidate mask of (plane, side) is complete
-    uint32_t* cand;         // [D][2][wwords]
+// Candidate pruning, per band.  An edge pixel P above the band that owns a pixel A of one of the band's rows is the
+// STRICTLY nearest edge pixel on the whole open segment from A to P (Voronoi cells are star-shaped around their site),
+// and that segment crosses the band's first row: on that row P's column has an interval of positive length on the
+// continuous lower envelope (P is also that column's vertical site there, or a nearer one in the column would beat it at
+// the crossing point).  The same holds for edge pixels below the band and the band's last row.  Hence
+//     columns with an edge pixel inside the band
+//   + survivors of a stack pass over the band's first row that only pops vertices which are nowhere strictly minimal
+//   + survivors of the same pass over its last row
+// is a superset of the owners of every row of the band, and all other columns can be skipped by the 32-row pass.
+// The two single-row passes are themselves parallel: lane = column segment, no join (a vertex of the row's envelope is
+// also a vertex of the envelope of its own segment); each lane remembers only its last kCandRing entries, older ones
+// stay candidates (tests/test_envelope_model.py::test_per_band_candidates_cover_every_row_of_the_band is the CPU model).
+constexpr int kCandRing = 8;
+
+struct LooseRing {
+    uint32_t ring0;         // shared address of this lane's slot 0 ([kCandRing][32] 8-byte slots, lane-interleaved)
+    int head, cnt;          // the ring holds cnt entries below the top, oldest in slot head
+    bool has;
+    uint32_t topkey;
+    int topv, tops;
+
+    __device__ __forceinline__ void init(uint32_t addr) { ring0 = addr; head = 0; cnt = 0; has = false; topkey = 0; topv = 0; tops = 0; }
+    static __device__ __forceinline__ void mark(uint32_t* cand, int v) { atomicOr(cand + (v >> 5), 1u << (v & 31)); }
+    __device__ __forceinline__ void column(int v, int gv, int Wm1, uint32_t* cand) {
+        const uint32_t key = (uint32_t)(gv * gv) + (uint32_t)(v * v);
+        int start = 0;
+        while (has) {
+            const int N = (int)key - (int)topkey;
+            const int Dn = 2 * (v - topv);
+            if (N < (tops - 1) * Dn) {            // the top is nowhere strictly minimal (see RowStack::take_over<kLoose>)
+                if (cnt > 0) {
+                    --cnt;
+                    const uint2 e = lds_u64(ring0 + (uint32_t)((head + cnt) & (kCandRing - 1)) * 256u);
+                    topkey = e.x;
+                    topv = (int)(e.y & 0xFFFFu);
+                    tops = (int)(e.y >> 16);
+                } else {
+                    has = false;                  // nothing remembered below: the next vertex starts at pixel 0
+                }
+                continue;
+            }
+            if (N >= Wm1 * Dn) return;            // takes over beyond the last pixel: owns nothing
+            start = RowStack::floor_div(N, Dn) + 1;
+            break;
+        }
+        if (has) {
+            if (cnt == kCandRing) {               // the oldest remembered entry leaves: it stays a candidate
+                mark(cand, (int)(lds_u64(ring0 + (uint32_t)head * 256u).y & 0xFFFFu));
+                head = (head + 1) & (kCandRing - 1);
+                --cnt;
+            }
+            sts_u64(ring0 + (uint32_t)((head + cnt) & (kCandRing - 1)) * 256u, make_uint2(topkey, (uint32_t)topv | ((uint32_t)tops << 16)));
+            ++cnt;
+        }
+        has = true;
+        topkey = key; topv = v; tops = start;
+    }
+    __device__ __forceinline__ void flush(uint32_t* cand) {
+        if (has) mark(cand, topv);
+        for (int i = 0; i < cnt; ++i) mark(cand, (int)(lds_u64(ring0 + (uint32_t)((head + i) & (kCandRing - 1)) * 256u).y & 0xFFFFu));
+    }
 };
+
+// shared memory of dt_row_band_kernel: [ring of the 32-row pass | aliased by the candidate phase: g of the band's first and
+// last row (u16 per column) + the loose rings] followed by the candidate column mask
+__host__ __device__ inline size_t band_alias_bytes(int pitch) {
+    const size_t ring = (size_t)2 * kRing * 32 * sizeof(uint2);
+    const size_t cand = (size_t)2 * pitch * sizeof(uint16_t) + (size_t)2 * kCandRing * 32 * sizeof(uint2);
+    return (ring > cand ? ring : cand + 15) / 16 * 16;
+}
 
 template <bool kFromG>
 __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict__ info, const uint16_t* __restrict__ g, MapDims dm,
                                                          int nbands, uint2* __restrict__ spill_all, int maxdepth,
-                                                         RowMeta* __restrict__ row_meta, int xsplit, BandAux aux, int n_cand_ctas, int band_lo,
-                                                         int band_hi) {
-    __shared__ __align__(16) uint2 ring_all[2][kRing * 32];
+                                                         RowMeta* __restrict__ row_meta, int xsplit, int band_lo, int band_hi) {
+    extern __shared__ __align__(16) unsigned char band_smem[];
     __shared__ int s_kright[32];
-    __shared__ int s_kleft;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring_all[warp]) + (uint32_t)lane * 8u;
+    uint2* ring_all = reinterpret_cast<uint2*>(band_smem);                                   // [2][kRing * 32]
+    uint32_t* s_cand = reinterpret_cast<uint32_t*>(band_smem + band_alias_bytes(dm.pitch)); // [wwords]
+    const uint32_t ring_addr = (uint32_t)__cvta_generic_to_shared(ring_all + (size_t)warp * kRing * 32) + (uint32_t)lane * 8u;
     const int Wm1 = dm.W - 1;
 
-    if ((int)blockIdx.x < n_cand_ctas) {
-        // ---- candidate pass of one (plane, side) ----
-        const int d = blockIdx.x >> 1, side = blockIdx.x & 1;
-        const int r_top = -aux.row_range[2 * d], r_bot = aux.row_range[2 * d + 1];
-        const int y0 = side == 0 ? r_top - 1 : r_bot + 1;
-        if (r_bot < 0 || y0 < 0 || y0 >= dm.H) {           // no edge in the plane, or no row on that side
-            if (threadIdx.x == 0) atomicExch(aux.flags + blockIdx.x, 1);
-            return;
-        }
-        const uint2* info_row = info + ((size_t)d * nbands + (y0 >> 5)) * dm.pitch + lane;
-        uint2* row_entries = spill_all + ((size_t)dm.D * nbands * 32 + blockIdx.x) * maxdepth;   // rows after the padded planes
-        RowStack st;
-        int kmine;
-        if (warp == 1) {
-            st.init(ring_addr, row_entries + (maxdepth - 1), -1);
-            envelope_half<false, true, true>(st, info_row, nullptr, nullptr, dm, d, y0 & ~31, xsplit, dm.pitch, lane, y0 & 31, nullptr);
-            kmine = st.park();
-            if (lane == 0) s_kright[0] = kmine;
-        } else {
-            st.init(ring_addr, row_entries, 1);
-            envelope_half<false, false, true>(st, info_row, nullptr, nullptr, dm, d, y0 & ~31, 0, xsplit, lane, y0 & 31, nullptr);
-            kmine = st.park();
-            if (lane == 0) s_kleft = kmine;
-        }
-        __syncthreads();
-        uint32_t* cw = aux.cand + (size_t)blockIdx.x * dm.wwords;
-        const int kl = s_kleft, kr = s_kright[0];
-        for (int i = threadIdx.x; i < kl + kr; i += blockDim.x) {
-            const uint2 e = i < kl ? row_entries[i] : row_entries[maxdepth - kr + (i - kl)];
-            const int v = (int)(e.y & 0xFFFFu);
-            atomicOr(cw + (v >> 5), 1u << (v & 31));
-        }
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicExch(aux.flags + blockIdx.x, 1);
-        return;
-    }
-
     // plane-fastest (neighbouring CTAs: different planes); the bands that overlap the scene's rows come first in the grid:
-    // they carry the long serial chains, the others mostly wait for their candidate mask
-    const int wg = blockIdx.x - n_cand_ctas;
-    const int d = wg % dm.D;
-    int b = wg / dm.D;
+    // they carry the long serial chains
+    const int d = blockIdx.x % dm.D;
+    int b = blockIdx.x / dm.D;
     {
         const int n_in = band_hi - band_lo + 1;
         b = b < n_in ? band_lo + b : (b - n_in < band_lo ? b - n_in : b);
@@ -381,31 +389,53 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
     uint2* row_entries = spill_all + prow * maxdepth;
 
     const uint32_t* cand = nullptr;
-    if (n_cand_ctas > 0) {
-        const int r_top = -aux.row_range[2 * d], r_bot = aux.row_range[2 * d + 1];
-        int side = -1;
-        if (r_bot >= 0) {
-            if (row0 + 31 < r_top) side = 0;                // the whole band lies above the first edge row
-            else if (row0 > r_bot) side = 1;                // ... below the last one
-        }
-        if (side >= 0) {                                    // (uniform over the CTA)
-            if (threadIdx.x == 0) {                         // one polling thread per CTA, long naps: the spin must not eat
-                volatile int32_t* f = aux.flags + 2 * d + side;   // the issue slots of the bands that do real work
-                while (*f == 0) __nanosleep(2000);
+    if (!kFromG) {
+        // ---- candidate phase: warp 0 takes the band's first row, warp 1 its last (existing) row ----
+        uint16_t* s_g = reinterpret_cast<uint16_t*>(band_smem) + (size_t)warp * dm.pitch;
+        const int rsel = warp == 0 ? 0 : min(31, dm.H - 1 - row0);
+        const uint32_t mle = 0xFFFFFFFFu >> (31 - rsel), mge = 0xFFFFFFFFu << rsel;
+        bool any = false;
+        for (int x0 = 0; x0 < dm.pitch; x0 += 32) {
+            const uint2 e = x0 + lane < dm.W ? info_row[x0] : make_uint2(0u, 0xFFFFFFFFu);
+            uint32_t gv = 0xFFFFu;
+            if (e.x != 0u || e.y != 0xFFFFFFFFu) {
+                const uint32_t above = e.x & mle, below = e.x & mge;
+                const int up = rsel + (above ? __clz(above) - 31 : (int)(e.y & 0xFFFFu));
+                const int dn = (31 - rsel) + (below ? __ffs(below) - 1 - 31 : (int)(e.y >> 16));
+                gv = (uint32_t)min(up, dn);
+                any = true;
             }
-            __syncthreads();
-            cand = aux.cand + (size_t)(2 * d + side) * dm.wwords;
+            s_g[x0 + lane] = (uint16_t)gv;
+            const uint32_t inside = __ballot_sync(0xffffffffu, e.x != 0u);
+            if (warp == 0 && lane == 0) s_cand[x0 >> 5] = inside;   // columns with an edge pixel inside the band
         }
+        __syncthreads();
+        // lane = column segment; the segment length in 16-bit words is 2 (mod 4): consecutive lanes hit different banks
+        int seg = (dm.W + 31) / 32;
+        seg += (2 - (seg & 3)) & 3;
+        LooseRing lr;
+        lr.init((uint32_t)__cvta_generic_to_shared(band_smem + (size_t)2 * dm.pitch * sizeof(uint16_t) +
+                                                   (size_t)warp * kCandRing * 32 * sizeof(uint2)) + (uint32_t)lane * 8u);
+        if (__any_sync(0xffffffffu, any)) {
+            const int v0 = lane * seg, v1 = min(dm.W, v0 + seg);
+            for (int v = v0; v < v1; ++v) {
+                const int gv = s_g[v];
+                if (gv != 0xFFFF) lr.column(v, gv, Wm1, s_cand);
+            }
+            lr.flush(s_cand);
+        }
+        __syncthreads();                                    // the mask is complete; the staging area becomes the ring
+        cand = s_cand;
     }
 
     RowStack st;
     if (warp == 1) {
         st.init(ring_addr, row_entries + (maxdepth - 1), -1);
-        envelope_half<kFromG, true, false>(st, info_row, g, g_row, dm, d, row0, xsplit, dm.pitch, lane, lane, cand);
+        envelope_half<kFromG, true>(st, info_row, g, g_row, dm, d, row0, xsplit, dm.pitch, lane, lane, cand);
         s_kright[lane] = st.park();
     } else {
         st.init(ring_addr, row_entries, 1);
-        envelope_half<kFromG, false, false>(st, info_row, g, g_row, dm, d, row0, 0, xsplit, lane, lane, cand);
+        envelope_half<kFromG, false>(st, info_row, g, g_row, dm, d, row0, 0, xsplit, lane, lane, cand);
     }
     __syncthreads();
     if (warp != 0) return;
@@ -853,40 +883,19 @@ static inline unsigned cdiv_u(size_t a, size_t b) { return (unsigned)((a + b - 1
 int dt_band_count(const MapDims& dm) { return (dm.H + 31) / 32; }
 size_t dt_band_info_bytes(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * dm.pitch * sizeof(uint2); }
 static size_t padded_rows(const MapDims& dm) { return (size_t)dm.D * dt_band_count(dm) * 32; }
-static size_t aux_ints(const MapDims& dm) { return (size_t)dm.D * 4 + (size_t)dm.D * 2 * dm.wwords; }   // row range, flags, masks
 static size_t row_k_bytes(const MapDims& dm) { return (padded_rows(dm) * sizeof(RowMeta) + 255) / 256 * 256; }
 // workspace of the row call: per-row RowMeta + per-row envelope array of maxdepth entries
 size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth) {
-    return row_k_bytes(dm) + (padded_rows(dm) + 2 * (size_t)dm.D) * (size_t)maxdepth * sizeof(uint2) + aux_ints(dm) * 4;
+    return row_k_bytes(dm) + padded_rows(dm) * (size_t)maxdepth * sizeof(uint2);
 }
 
-static BandAux band_aux(const MapDims& dm, void* d_ws, int maxdepth) {
-    unsigned char* p = reinterpret_cast<unsigned char*>(d_ws) + row_k_bytes(dm) +
-                       (padded_rows(dm) + 2 * (size_t)dm.D) * (size_t)maxdepth * sizeof(uint2);
-    BandAux a;
-    a.row_range = reinterpret_cast<int32_t*>(p);
-    a.flags = a.row_range + 2 * dm.D;
-    a.cand = reinterpret_cast<uint32_t*>(a.flags + 2 * dm.D);
-    return a;
-}
-
-// d_ws / maxdepth: the row-call workspace when the plane row ranges are wanted (candidate pruning), else nullptr
-void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
-    int32_t* row_range = nullptr;
-    if (d_ws) {
-        int lo = win_lo < 0 ? 0 : win_lo, hi = win_hi >= dm.W ? dm.W - 1 : win_hi;
-        if (hi < lo) { lo = 0; hi = dm.W - 1; }
-        const BandAux a = band_aux(dm, d_ws, hi - lo + 1);
-        cudaMemsetAsync(a.row_range, 0x80, (size_t)dm.D * 2 * 4, s);                                 // very negative
-        cudaMemsetAsync(a.flags, 0, ((size_t)dm.D * 2 + (size_t)dm.D * 2 * dm.wwords) * 4, s);       // flags + masks
-        row_range = a.row_range;
-    }
+void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, cudaStream_t s) {
     const int nbands = dt_band_count(dm);
     const size_t smem = (size_t)nbands * 64 * 6;
     dim3 grid((dm.wwords + 1) / 2, dm.D);
     // (set per call: the attribute is per device and a process may drive several devices)
     if (smem > 48 * 1024) cudaFuncSetAttribute(dt_col_band_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dt_col_band_kernel<<<grid, 256, smem, s>>>(d_mask, dm, reinterpret_cast<uint2*>(d_info), nbands, row_range);
+    dt_col_band_kernel<<<grid, 256, smem, s>>>(d_mask, dm, reinterpret_cast<uint2*>(d_info), nbands);
 }
 
 // [win_lo, win_hi]: columns that can hold an edge pixel (envelope vertices only exist there)
@@ -907,14 +916,15 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
     const int xsplit = min(dm.pitch, max(0, ((ws.win_lo + ws.win_lo + ws.maxdepth) / 2) & ~31));
     int band_lo = (row_lo < 0 ? 0 : row_lo) >> 5, band_hi = (row_hi >= dm.H ? dm.H - 1 : row_hi) >> 5;
     if (band_hi < band_lo || band_hi >= nbands) { band_lo = 0; band_hi = nbands - 1; }
+    const size_t smem = band_alias_bytes(dm.pitch) + (size_t)dm.wwords * sizeof(uint32_t);
     if (d_g) {
-        dt_row_band_kernel<true><<<(unsigned)(dm.D * nbands), 64, 0, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
-                                                                          BandAux{nullptr, nullptr, nullptr}, 0, band_lo, band_hi);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(dt_row_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dt_row_band_kernel<true><<<(unsigned)(dm.D * nbands), 64, smem, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
+                                                                             band_lo, band_hi);
     } else {
-        const int n_cand = 2 * dm.D;
-        dt_row_band_kernel<false><<<(unsigned)(dm.D * nbands + n_cand), 64, 0, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
-                                                                                    ws.spill, ws.maxdepth, ws.row_k, xsplit,
-                                                                                    band_aux(dm, d_ws, ws.maxdepth), n_cand, band_lo, band_hi);
+        if (smem > 48 * 1024) cudaFuncSetAttribute(dt_row_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        dt_row_band_kernel<false><<<(unsigned)(dm.D * nbands), 64, smem, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
+                                                                              ws.spill, ws.maxdepth, ws.row_k, xsplit, band_lo, band_hi);
     }
 }
 
@@ -954,7 +964,8 @@ void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& 
 size_t dt_band_smem_bytes(const MapDims& dm) {
     const size_t col = (size_t)dt_band_count(dm) * 64 * 6;
     const size_t l1 = (size_t)30 * FPConfig<30>::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch >> 5) + 1) * sizeof(int);
-    return col > l1 ? col : l1;
+    const size_t env = band_alias_bytes(dm.pitch) + (size_t)dm.wwords * sizeof(uint32_t);
+    return std::max(std::max(col, l1), env);
 }
 
 }   // namespace fdcm

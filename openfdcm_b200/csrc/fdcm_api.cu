@@ -558,7 +558,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
     if (m->band_l1) {
         {
             KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
-            launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, nullptr, 0, 0, s);
+            launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, s);
         }
         fused_propagate = m->stage != 1 && dt_fill_propagate_supported(dm);
         if (fused_propagate) {
@@ -571,7 +571,7 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
     } else if (m->band_path) {
         {
             KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
-            launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, m->band_spill.p, m->col_lo, m->col_hi, s);
+            launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, s);
         }
         {
             KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);

@@ -34,8 +34,7 @@ void launch_integral_tma(float* d_planes, const MapDims& dm, const IntegralParam
 int dt_band_count(const MapDims& dm);
 size_t dt_band_info_bytes(const MapDims& dm);
 size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth);
-// d_ws (row-call workspace, may be null): also records every plane's first / last edge row there (candidate pruning)
-void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
+void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, cudaStream_t s);
 // d_info (band records) or d_g (explicit u16 rows, tests) feeds the envelope build; exactly one of them is non-null
 // [row_lo, row_hi]: rows that can hold edge pixels (only used to order the bands in the grid)
 void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi, int row_lo,
