@@ -97,6 +97,7 @@ typedef struct fdcm_search_stats {
 
 typedef struct fdcm_dt3 fdcm_dt3;               /* device feature map: [depth][height][pitch] fp32 planes */
 typedef struct fdcm_templates fdcm_templates;   /* device-resident template set */
+typedef struct fdcm_comm fdcm_comm;             /* multi-GPU communicator of one rank (one process per GPU, NCCL) */
 
 const char* fdcm_last_error(void);
 int32_t fdcm_abi_version(void);
@@ -208,6 +209,32 @@ fdcm_status fdcm_penalize(int32_t penalty_kind, float tau, fdcm_match* matches, 
 fdcm_status fdcm_sort_matches(fdcm_match* matches, int64_t n);
 /* getTemplateLengths without a device */
 fdcm_status fdcm_template_lengths(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, float* lengths);
+
+/* ---- multi-GPU: one process per GPU, templates sharded by tmpl_idx, NCCL over NVLink ------------
+ * The reference has no distributed code; these entry points are what a multi-GPU host (C++ or Python) calls instead of
+ * looping search() over template blocks.  NCCL is resolved at run time (dlopen of libnccl.so.2); without it every
+ * fdcm_comm_* call returns FDCM_ERR_CUDA.  Bootstrap like NCCL itself: rank 0 creates the id, the application ships the
+ * 128 bytes to the other ranks (MPI, a file, torch.distributed ...), every rank calls fdcm_comm_init. */
+#define FDCM_COMM_ID_BYTES 128
+fdcm_status fdcm_comm_unique_id(uint8_t id[FDCM_COMM_ID_BYTES]);
+fdcm_status fdcm_comm_init(const uint8_t id[FDCM_COMM_ID_BYTES], int32_t rank, int32_t world, int32_t device, fdcm_comm** out);
+fdcm_status fdcm_comm_destroy(fdcm_comm* comm);
+fdcm_status fdcm_comm_info(const fdcm_comm* comm, int32_t* rank, int32_t* world);
+/* contiguous block [begin, end) of `n_items` templates (or scenes) owned by `rank`: global tmpl_idx = begin + local index */
+fdcm_status fdcm_comm_shard(int32_t n_items, int32_t rank, int32_t world, int32_t* begin, int32_t* end);
+/* fdcm_search (top_k > 0) of this rank's template shard (params->tmpl_idx_base = first global index of the shard), then
+ * the exchange on the device: ncclAllGather of the k x 32-byte top-K buffer on the compute stream, an R*k -> k merge
+ * kernel (ascending score, ties by rank then position = global hypothesis order), one download.  Every rank returns the
+ * same global top-k.  Collective: every rank must call it, also with an empty shard. */
+fdcm_status fdcm_comm_search_topk(fdcm_comm* comm, const fdcm_dt3* map, const fdcm_templates* shard, const float* scene_xyxy,
+                                  int32_t n_scene, const fdcm_search_params* params, fdcm_match* out, int64_t capacity,
+                                  int64_t* n_out);
+/* fdcm_dt3_rebuild on every rank with the kernels run on `root` only and the planes sent by ncclBroadcast (collective):
+ * the alternative to every rank building the scene's map itself; bench.py measures both. */
+fdcm_status fdcm_comm_rebuild_broadcast(fdcm_comm* comm, fdcm_dt3* map, const float* scene_xyxy, int32_t n_lines, int32_t root);
+/* worker threads of the host-side template preparation (std::sort per template); 0 = default.  fdcm_comm_init sets
+ * cores / world when it is still at the default so that the ranks of one host do not oversubscribe it. */
+fdcm_status fdcm_set_host_threads(int32_t n);
 
 /* ---- per-kernel timing (CUDA events on the launching stream; feeds bench.py's roofline) ------ */
 fdcm_status fdcm_profile_enable(int32_t on);

@@ -85,6 +85,14 @@ SIGNATURES = {
                                    C.POINTER(C.c_double)]),
     "fdcm_profile_count": (C.c_int, [C.POINTER(C.c_int32)]),
     "fdcm_kernel_launch_count": (C.c_int64, []),
+    "fdcm_comm_unique_id": (C.c_int, [_P]),
+    "fdcm_comm_init": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "fdcm_comm_destroy": (C.c_int, [_P]),
+    "fdcm_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fdcm_comm_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "fdcm_comm_search_topk": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(SearchParams), _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "fdcm_comm_rebuild_broadcast": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32]),
+    "fdcm_set_host_threads": (C.c_int, [C.c_int32]),
 }
 
 

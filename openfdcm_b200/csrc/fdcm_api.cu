@@ -994,8 +994,10 @@ public:
     }
 };
 
+static int g_host_threads = 0;   // 0: default (min(16, cores)); takes effect before the first template preparation
 static HostPool& host_pool() {
-    static HostPool pool((int)std::min(15u, std::max(1u, std::thread::hardware_concurrency()) - 1));
+    // workers besides the calling thread; fdcm_set_host_threads / fdcm_comm_init bound it (one process per GPU shares a host)
+    static HostPool pool(std::max(0, std::min(15, (g_host_threads > 0 ? g_host_threads : (int)std::max(1u, std::thread::hardware_concurrency())) - 1)));
     return pool;
 }
 static std::mutex g_pool_mutex;   // one parallel_for at a time
@@ -1121,6 +1123,135 @@ extern "C" fdcm_status fdcm_template_lengths(const float* tl, const int32_t* off
     return FDCM_OK;
 }
 
+
+// =============================================================================================
+// multi-GPU: one process per GPU, NCCL resolved at run time (dlopen: the library has no hard NCCL dependency, and a
+// process that already loaded torch's NCCL shares that copy through the SONAME)
+// =============================================================================================
+#include <dlfcn.h>
+#include <nccl.h>   // types only
+
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static const NcclApi& nccl_api() {
+    static const NcclApi api = [] {
+        NcclApi a;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) return a;
+        a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+        a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+        a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+        a.AllGather = (decltype(a.AllGather))dlsym(h, "ncclAllGather");
+        a.Broadcast = (decltype(a.Broadcast))dlsym(h, "ncclBroadcast");
+        a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+        a.ok = a.GetUniqueId && a.CommInitRank && a.CommDestroy && a.AllGather && a.Broadcast && a.GetErrorString;
+        return a;
+    }();
+    return api;
+}
+#define NCCL_TRY(expr)                                                                                     \
+    do {                                                                                                   \
+        ncclResult_t _r = (expr);                                                                          \
+        if (_r != ncclSuccess) return fail(FDCM_ERR_CUDA, std::string(#expr) + ": " + nccl_api().GetErrorString(_r)); \
+    } while (0)
+
+struct fdcm_comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, world = 1, device = 0;
+    DevBuf gather, merged, merged_n;
+    ~fdcm_comm() {
+        cudaSetDevice(device);
+        for (DevBuf* b : {&gather, &merged, &merged_n}) b->release();
+        if (comm) nccl_api().CommDestroy(comm);
+    }
+};
+
+extern "C" fdcm_status fdcm_comm_unique_id(uint8_t id[FDCM_COMM_ID_BYTES]) {
+    if (!id) return fail(FDCM_ERR_INVALID, "id is null");
+    static_assert(FDCM_COMM_ID_BYTES == NCCL_UNIQUE_ID_BYTES, "id size");
+    if (!nccl_api().ok) return fail(FDCM_ERR_CUDA, "NCCL (libnccl.so.2) is not available");
+    ncclUniqueId u;
+    NCCL_TRY(nccl_api().GetUniqueId(&u));
+    std::memcpy(id, u.internal, NCCL_UNIQUE_ID_BYTES);
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_set_host_threads(int32_t n) {
+    if (n < 0) return fail(FDCM_ERR_INVALID, "bad thread count");
+    g_host_threads = n;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_comm_init(const uint8_t id[FDCM_COMM_ID_BYTES], int32_t rank, int32_t world, int32_t device, fdcm_comm** out) {
+    if (!out) return fail(FDCM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(FDCM_ERR_INVALID, "bad communicator arguments");
+    if (!nccl_api().ok) return fail(FDCM_ERR_CUDA, "NCCL (libnccl.so.2) is not available");
+    CUDA_TRY(cudaSetDevice(device));
+    fdcm_comm* c = new (std::nothrow) fdcm_comm();
+    if (!c) return fail(FDCM_ERR_NOMEM, "host allocation failed");
+    c->rank = rank; c->world = world; c->device = device;
+    ncclUniqueId u;
+    std::memcpy(u.internal, id, NCCL_UNIQUE_ID_BYTES);
+    ncclResult_t r = nccl_api().CommInitRank(&c->comm, world, u, rank);
+    if (r != ncclSuccess) {
+        c->comm = nullptr;
+        delete c;
+        return fail(FDCM_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r));
+    }
+    // one process per GPU on one host: share the host cores between the ranks' template-preparation pools
+    if (g_host_threads == 0) g_host_threads = std::max(1, (int)std::thread::hardware_concurrency() / world);
+    *out = c;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_comm_destroy(fdcm_comm* c) {
+    delete c;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_comm_info(const fdcm_comm* c, int32_t* rank, int32_t* world) {
+    if (!c) return fail(FDCM_ERR_INVALID, "comm is null");
+    if (rank) *rank = c->rank;
+    if (world) *world = c->world;
+    return FDCM_OK;
+}
+
+// contiguous template block of a rank (global tmpl_idx = begin + local index; ties of the merged top-k then resolve
+// in global hypothesis order)
+extern "C" fdcm_status fdcm_comm_shard(int32_t n_items, int32_t rank, int32_t world, int32_t* begin, int32_t* end) {
+    if (!begin || !end || n_items < 0 || world < 1 || rank < 0 || rank >= world) return fail(FDCM_ERR_INVALID, "bad argument");
+    const int64_t q = n_items / world, r = n_items % world;
+    *begin = (int32_t)(rank * q + std::min<int64_t>(rank, r));
+    *end = (int32_t)(*begin + q + (rank < r ? 1 : 0));
+    return FDCM_OK;
+}
+
+// device-side exchange of the ranks' top-k: ncclAllGather of the k x 32-byte buffer the top-K kernels just wrote, on the
+// compute stream, then an R*k -> k merge kernel; the caller downloads the merged list
+static fdcm_status comm_merge_topk(fdcm_comm* c, const fdcm_dt3* m, int k, cudaStream_t s, const fdcm_match** d_result, const int** d_n) {
+    if (c->device != m->device) return fail(FDCM_ERR_INVALID, "communicator and feature map live on different devices");
+    CUDA_TRY(c->gather.reserve((size_t)c->world * k * sizeof(fdcm_match)));
+    CUDA_TRY(c->merged.reserve((size_t)k * sizeof(fdcm_match)));
+    CUDA_TRY(c->merged_n.reserve(4));
+    NCCL_TRY(nccl_api().AllGather(m->s_topk_out.p, c->gather.p, (size_t)k * sizeof(fdcm_match), ncclChar, c->comm, s));
+    {
+        KernelScope ks("topk_merge", 0.0, s, 1);
+        launch_topk_merge(c->gather.as<fdcm_match>(), c->world * k, k, c->merged.as<fdcm_match>(), c->merged_n.as<int>(), s);
+    }
+    *d_result = c->merged.as<fdcm_match>();
+    *d_n = c->merged_n.as<int>();
+    return FDCM_OK;
+}
+
 // =============================================================================================
 // search
 // =============================================================================================
@@ -1129,10 +1260,42 @@ static float penalty_denominator(int kind, float tau, float length) {
     return kind == FDCM_PENALTY_DEFAULT ? len : std::pow(len, tau);   // defaultpenalty.cpp:39 / exponentialpenalty.cpp:43
 }
 
-extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, const float* scene, int32_t n_scene,
-                                   const fdcm_search_params* p, fdcm_match* out, int64_t capacity, int64_t* n_out) {
+// download of the (possibly merged) top-k list at the end of a search
+static fdcm_status finish_topk(const fdcm_dt3* m, fdcm_comm* comm, int k, cudaStream_t s, unsigned long long* counters, fdcm_match* out,
+                               int64_t capacity, int64_t* n_out) {
+    const fdcm_match* d_result = m->s_topk_out.as<fdcm_match>();
+    const int* d_n = m->s_topk_n.as<int>();
+    if (comm)
+        if (fdcm_status st = comm_merge_topk(comm, m, k, s, &d_result, &d_n)) return st;
+    int n_sel = 0;
+    std::vector<fdcm_match> sel((size_t)k);
+    CUDA_TRY(cudaMemcpyAsync(&n_sel, d_n, 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(sel.data(), d_result, (size_t)k * sizeof(fdcm_match), cudaMemcpyDeviceToHost, s));
+    if (counters) CUDA_TRY(cudaMemcpyAsync(counters, m->s_counters.p, 3 * 8, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    *n_out = n_sel;
+    if (n_sel > capacity || (n_sel > 0 && !out)) return fail(FDCM_ERR_CAPACITY, "output buffer too small");
+    if (n_sel > 0) std::memcpy(out, sel.data(), (size_t)n_sel * sizeof(fdcm_match));
+    return FDCM_OK;
+}
+
+// a rank whose shard yields no hypothesis still takes part in the exchange
+static fdcm_status exchange_empty(const fdcm_dt3* m, fdcm_comm* comm, int k, fdcm_match* out, int64_t capacity, int64_t* n_out) {
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    CUDA_TRY(m->s_topk_out.reserve((size_t)k * sizeof(fdcm_match)));
+    CUDA_TRY(m->s_topk_n.reserve(4));
+    launch_topk_invalid(m->s_topk_out.as<fdcm_match>(), k, m->s_topk_n.as<int>(), s);
+    return finish_topk(m, comm, k, s, nullptr, out, capacity, n_out);
+}
+
+static fdcm_status search_impl(const fdcm_dt3* m, const fdcm_templates* tc, const float* scene, int32_t n_scene,
+                               const fdcm_search_params* p, fdcm_match* out, int64_t capacity, int64_t* n_out, fdcm_comm* comm) {
     if (!m || !tc || !p || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
     *n_out = 0;
+    if (comm && p->top_k <= 0) return fail(FDCM_ERR_INVALID, "the multi-GPU search needs top_k > 0");
+#define FDCM_NO_LOCAL_MATCHES() do { if (comm) return exchange_empty(m, comm, p->top_k, out, capacity, n_out); return FDCM_OK; } while (0)
     if (p->max_tmpl_lines < 0 || p->max_scene_lines < 0 || p->batch_size < 0 || p->top_k < 0 || p->penalty_kind < 0 ||
         p->penalty_kind > 2)
         return fail(FDCM_ERR_INVALID, "bad search parameters");
@@ -1151,7 +1314,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
         scene = m->h_build_scene.data();
         n_scene = (int32_t)(m->h_build_scene.size() / 4);
     }
-    if (t->n_tmpl == 0 || n_scene <= 0 || (m->dm.W == 0 && m->dm.H == 0)) return FDCM_OK;
+    if (t->n_tmpl == 0 || n_scene <= 0 || (m->dm.W == 0 && m->dm.H == 0)) FDCM_NO_LOCAL_MATCHES();
     if (m->stage != 0) return fail(FDCM_ERR_INVALID, "feature map was built with a debug stage");
     CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t s;
@@ -1167,7 +1330,7 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
         m->s_resident_is_build = resident_scene;
     }
     n_scene = m->s_sorted_n;   // the lines that take part in the length matching
-    if (n_scene <= 0) return FDCM_OK;   // concentricrange.cpp:37-38
+    if (n_scene <= 0) FDCM_NO_LOCAL_MATCHES();   // concentricrange.cpp:37-38
     const int nS = std::min<int>(n_scene, p->max_scene_lines);
     std::vector<int64_t> hyp_off((size_t)t->n_tmpl + 1, 0);
     for (int i = 0; i < t->n_tmpl; ++i) {
@@ -1177,7 +1340,8 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     const int64_t H = hyp_off[(size_t)t->n_tmpl];
     m->last_n_hyp = H;
     m->last_stats.n_hypotheses = H;
-    if (H == 0) return FDCM_OK;
+    if (H == 0) FDCM_NO_LOCAL_MATCHES();
+#undef FDCM_NO_LOCAL_MATCHES
 
     // ---- workspace ----
     CUDA_TRY(m->s_hyp_off.reserve(hyp_off.size() * 8));
@@ -1285,15 +1449,8 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
                         m->s_topk_out.as<fdcm_match>(), m->s_topk_n.as<int>(), s);
         }
         CUDA_TRY(cudaGetLastError());
-        int n_sel = 0;
-        std::vector<fdcm_match> sel((size_t)k);
-        CUDA_TRY(cudaMemcpyAsync(&n_sel, m->s_topk_n.p, 4, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(sel.data(), m->s_topk_out.p, (size_t)k * sizeof(fdcm_match), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(counters, m->s_counters.p, 3 * 8, cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
-        *n_out = n_sel;
-        if (n_sel > capacity || (n_sel > 0 && !out)) result = fail(FDCM_ERR_CAPACITY, "output buffer too small");
-        else if (n_sel > 0) std::memcpy(out, sel.data(), (size_t)n_sel * sizeof(fdcm_match));
+        result = finish_topk(m, comm, k, s, counters, out, capacity, n_out);
+        if (result != FDCM_OK && result != FDCM_ERR_CAPACITY) return result;
     } else {
         // every match in hypothesis order: download records + flags, compact on the host
         const size_t need = (size_t)H * sizeof(fdcm_match) + (size_t)H;
@@ -1325,6 +1482,50 @@ extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, 
     m->last_stats.n_lookups = (int64_t)counters[1];
     m->last_stats.n_valid = (int64_t)counters[2];
     return result;
+}
+
+extern "C" fdcm_status fdcm_search(const fdcm_dt3* m, const fdcm_templates* tc, const float* scene, int32_t n_scene,
+                                   const fdcm_search_params* p, fdcm_match* out, int64_t capacity, int64_t* n_out) {
+    return search_impl(m, tc, scene, n_scene, p, out, capacity, n_out, nullptr);
+}
+
+// fdcm_search of this rank's template shard (params->tmpl_idx_base = first global index of the shard) followed by the
+// device-side exchange: every rank returns the same global top-k.  Collective: every rank of the communicator must call it.
+extern "C" fdcm_status fdcm_comm_search_topk(fdcm_comm* comm, const fdcm_dt3* m, const fdcm_templates* shard, const float* scene,
+                                             int32_t n_scene, const fdcm_search_params* p, fdcm_match* out, int64_t capacity,
+                                             int64_t* n_out) {
+    if (!comm) return fail(FDCM_ERR_INVALID, "comm is null");
+    return search_impl(m, shard, scene, n_scene, p, out, capacity, n_out, comm);
+}
+
+// Scene feature map on every rank without building it everywhere: all ranks run the O(#lines) host preparation of the same
+// scene, `root` runs the build kernels, the planes travel by ncclBroadcast (NVLink).  Collective.  north_star: "each rank
+// builds the scene's feature map itself, or it is NCCL-broadcast over NVLink, whichever measures faster".
+extern "C" fdcm_status fdcm_comm_rebuild_broadcast(fdcm_comm* comm, fdcm_dt3* m, const float* scene_xyxy, int32_t n_lines, int32_t root) {
+    if (!comm || !m) return fail(FDCM_ERR_INVALID, "null argument");
+    if (root < 0 || root >= comm->world) return fail(FDCM_ERR_INVALID, "bad root");
+    if (n_lines < 0 || (n_lines > 0 && !scene_xyxy)) return fail(FDCM_ERR_INVALID, "bad scene");
+    if (m->stage != 0) return fail(FDCM_ERR_INVALID, "feature map was built with a debug stage");
+    CUDA_TRY(cudaSetDevice(m->device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(m->device, &s)) return st;
+    std::lock_guard<std::mutex> lk(m->search_mutex);
+    fdcm_status st = prepare_and_upload(m, scene_xyxy, n_lines, s);
+    if (st == FDCM_OK && comm->rank == root) st = run_build_kernels(m, s);
+    if (st == FDCM_OK && n_lines > 0) {
+        const size_t bytes = (size_t)m->dm.D * m->dm.plane_elems * sizeof(float);
+        ncclResult_t r = nccl_api().Broadcast(m->planes.p, m->planes.p, bytes, ncclChar, root, comm->comm, s);
+        if (r != ncclSuccess) st = fail(FDCM_ERR_CUDA, std::string("ncclBroadcast: ") + nccl_api().GetErrorString(r));
+    }
+    if (st == FDCM_OK) st = upload_build_scene(m, scene_xyxy, n_lines, s);
+    if (st == FDCM_OK && cudaStreamSynchronize(s) != cudaSuccess) st = fail(FDCM_ERR_CUDA, "rebuild_broadcast: stream failed");
+    prof_resolve();
+    if (st != FDCM_OK) {
+        const std::string msg = g_last_error;
+        invalidate_map(m);
+        g_last_error = msg;
+    }
+    return st;
 }
 
 // optimize(optimizer, templates, alignments, featuremap) (matching/optimizestrategy.h:62-64;

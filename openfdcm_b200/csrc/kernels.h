@@ -105,6 +105,9 @@ void launch_search(const MapView& map, const SlopeTableDev& table, const Templat
 void launch_topk(const fdcm_match* d_rec, const uint8_t* d_valid, int64_t n, int k, float* d_ws_score, int64_t* d_ws_idx,
                  int ws_blocks, fdcm_match* d_out, int* d_n_out, cudaStream_t s);
 int topk_ws_blocks(int64_t n);
+// multi-GPU: merge of the all-gathered per-rank top-k lists; k invalid records for an empty shard
+void launch_topk_merge(const fdcm_match* d_gathered, int n_cand, int k, fdcm_match* d_out, int* d_n_out, cudaStream_t s);
+void launch_topk_invalid(fdcm_match* d_out, int k, int* d_n_out, cudaStream_t s);
 
 void launch_evaluate(const MapView& map, const SlopeTableDev& table, const float4* d_lines, const int32_t* d_toff,
                      const float2* d_transl, const int32_t* d_troff, const int32_t* d_owner, int64_t n_scores,

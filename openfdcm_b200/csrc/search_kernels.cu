@@ -483,8 +483,58 @@ __global__ void __launch_bounds__(1024) topk_level2_kernel(const fdcm_match* __r
         last = best;
         ++produced;
     }
+    // unused slots: invalid records (tmpl_idx -1, score +inf), so that the k-record buffer can be exchanged as it is
+    for (int q = produced + threadIdx.x; q < k; q += blockDim.x) {
+        fdcm_match m;
+        m.tmpl_idx = -1;
+        m.score = INFINITY;
+        for (int i = 0; i < 6; ++i) m.transform[i] = 0.f;
+        out[q] = m;
+    }
     if (threadIdx.x == 0) *n_out = produced;
 }
+
+// merge of the ranks' top-k lists (all-gathered, rank-major): the k best of R*k records, ascending score, ties by
+// (rank, position in the rank's list) = global hypothesis order when templates are sharded in contiguous blocks
+__global__ void __launch_bounds__(256) topk_merge_kernel(const fdcm_match* __restrict__ gathered, int n_cand, int k,
+                                                         fdcm_match* __restrict__ out, int* __restrict__ n_out) {
+    __shared__ Key s_keys[32];
+    Key last{-INFINITY, -1};
+    int produced = 0;
+    for (int r = 0; r < k; ++r) {
+        Key best{INFINITY, LLONG_MAX};
+        for (int i = threadIdx.x; i < n_cand; i += blockDim.x) {
+            if (gathered[i].tmpl_idx < 0) continue;
+            float s = gathered[i].score;
+            if (s != s) s = INFINITY;
+            const Key c{s, (long long)i};
+            if (key_less(last, c) && key_less(c, best)) best = c;
+        }
+        best = block_min_key(best, s_keys);
+        if (best.i == LLONG_MAX) break;
+        if (threadIdx.x == 0) out[r] = gathered[best.i];
+        last = best;
+        ++produced;
+    }
+    if (threadIdx.x == 0) *n_out = produced;
+}
+
+void launch_topk_merge(const fdcm_match* d_gathered, int n_cand, int k, fdcm_match* d_out, int* d_n_out, cudaStream_t s) {
+    topk_merge_kernel<<<1, 256, 0, s>>>(d_gathered, n_cand, k, d_out, d_n_out);
+}
+
+// an empty shard still takes part in the exchange: k invalid records
+__global__ void topk_invalid_kernel(fdcm_match* __restrict__ out, int k, int* __restrict__ n_out) {
+    for (int q = threadIdx.x; q < k; q += blockDim.x) {
+        fdcm_match m;
+        m.tmpl_idx = -1;
+        m.score = INFINITY;
+        for (int i = 0; i < 6; ++i) m.transform[i] = 0.f;
+        out[q] = m;
+    }
+    if (threadIdx.x == 0) *n_out = 0;
+}
+void launch_topk_invalid(fdcm_match* d_out, int k, int* d_n_out, cudaStream_t s) { topk_invalid_kernel<<<1, 256, 0, s>>>(d_out, k, d_n_out); }
 
 int topk_ws_blocks(int64_t n) {
     const int64_t per_block = 1024 * 2;

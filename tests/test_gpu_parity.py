@@ -493,3 +493,22 @@ def test_two_devices_in_one_process():
         assert np.array_equal(g.plane(11), c.plane(11))
         got = fdcm.search_all(g, fdcm.TemplateSet(tmpls, device=dev), scene, fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10))
         assert np.array_equal(got["score"], want["score"])
+
+
+def test_comm_world1_device_merge():
+    """fdcm_comm_* with a single rank: the NCCL all-gather + merge kernel path returns the plain top-k."""
+    from openfdcm_b200 import distributed as fd
+    scene, tmpls = _workload(77, n_tmpl=40, n_lines=25)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    comm = fd.Communicator(fd.Communicator.unique_id(), 0, 1, 0)
+    assert comm.shard(40) == (0, 40)
+    s, o, p = fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5)
+    want = fdcm.search_topk(g, tmpls, scene, s, o, p, k=10)
+    got = comm.search_topk(g, fdcm.TemplateSet(tmpls), scene, s, o, p, 10, 0)
+    assert np.array_equal(got, want)
+    # fewer matches than k, and an empty shard
+    assert np.array_equal(comm.search_topk(g, fdcm.TemplateSet(tmpls[:1]), None, s, o, p, 50, 0), fdcm.search_topk(g, tmpls[:1], None, s, o, p, k=50))
+    assert len(comm.search_topk(g, fdcm.TemplateSet([]), None, s, o, p, 10, 0)) == 0
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    comm.rebuild_broadcast(g, scene, root=0)
+    assert np.array_equal(g.plane(7), c.plane(7))
