@@ -11,6 +11,7 @@
 // column-major memory of the reference's Eigen::Matrix<float,4,-1> (core/math.h:66); INTEGRATION.md shows the
 // two-line adapters that plug these functions into the reference's type-erased FeatureMap / strategies.
 #pragma once
+#include <algorithm>
 #include <array>
 #include <cstdint>
 #include <memory>
@@ -180,15 +181,15 @@ struct DefaultPenalty {};
 struct ExponentialPenalty { float tau; float getTau() const noexcept { return tau; } };
 
 namespace detail {
-inline std::vector<Match> search(int batch, const DefaultSearch& s, const Dt3Cuda& fm, const std::vector<LineArray>& templates,
-                                 const LineArray& scene, int penalty_kind, float tau, int top_k) {
+inline std::vector<Match> search_raw(const fdcm_search_params& p, const Dt3Cuda& fm, const std::vector<LineArray>& templates,
+                                     const LineArray& scene) {
     std::vector<float> flat;
     std::vector<int32_t> off;
     pack(templates, flat, off);
-    fdcm_search_params p{(int32_t)s.max_tmpl_lines, (int32_t)s.max_scene_lines, batch, penalty_kind, tau, top_k, 0, 0, 0.f, 0.f, 0.f, 0.f};
+    const int top_k = p.top_k;
     int64_t cap = top_k > 0 ? top_k : 0;
     if (top_k <= 0)
-        for (const auto& t : templates) cap += 2 * (int64_t)std::min(t.size() / 4, s.max_tmpl_lines) * (int64_t)s.max_scene_lines;
+        for (const auto& t : templates) cap += 2 * (int64_t)std::min<size_t>(t.size() / 4, (size_t)p.max_tmpl_lines) * (int64_t)p.max_scene_lines;
     std::vector<fdcm_match> rec((size_t)std::max<int64_t>(cap, 1));
     int64_t n = 0;
     check(fdcm_search_host(fm.handle(), flat.data(), off.data(), (int32_t)templates.size(), scene.data(), (int32_t)(scene.size() / 4),
@@ -200,6 +201,18 @@ inline std::vector<Match> search(int batch, const DefaultSearch& s, const Dt3Cud
         for (int k = 0; k < 6; ++k) out[(size_t)i].transform[(size_t)k] = rec[(size_t)i].transform[k];
     }
     return out;
+}
+inline std::vector<Match> search(int batch, const DefaultSearch& s, const Dt3Cuda& fm, const std::vector<LineArray>& templates,
+                                 const LineArray& scene, int penalty_kind, float tau, int top_k) {
+    const fdcm_search_params p{(int32_t)s.max_tmpl_lines, (int32_t)s.max_scene_lines, batch, penalty_kind, tau, top_k, 0, 0, 0.f, 0.f, 0.f, 0.f};
+    return search_raw(p, fm, templates, scene);
+}
+template <class Concentric>   // ConcentricRangeStrategy (strategies.hpp)
+inline std::vector<Match> search_concentric(int batch, const Concentric& s, const Dt3Cuda& fm, const std::vector<LineArray>& templates,
+                                            const LineArray& scene) {
+    const fdcm_search_params p{(int32_t)s.max_tmpl_lines, (int32_t)s.max_scene_lines, batch, FDCM_PENALTY_NONE, 0.f, 0, 0, 1,
+                               s.center_position.x, s.center_position.y, s.low_boundary, s.high_boundary};
+    return search_raw(p, fm, templates, scene);
 }
 }   // namespace detail
 

@@ -512,3 +512,19 @@ def test_comm_world1_device_merge():
     c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
     comm.rebuild_broadcast(g, scene, root=0)
     assert np.array_equal(g.plane(7), c.plane(7))
+
+
+def test_cpp_type_erased_strategies():
+    """tests/cpp/test_type_erasure.cpp: FeatureMap / SearchStrategy / OptimizeStrategy / MatchStrategy / PenaltyStrategy
+    (Concept / Model + clone, featuremap.h:57-124, matchstrategy.h:83-140) over the CUDA types; fused path == generic
+    composition == clones."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "test_type_erasure")
+    if not os.path.exists(exe):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"), exe + ".cpp", "-L" + os.path.join(root, "openfdcm_b200"),
+                               "-lfdcm_b200", "-Wl,-rpath,$ORIGIN/../../openfdcm_b200", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "fused == generic == cloned" in r.stdout
