@@ -62,7 +62,7 @@ int main() {
         generic = search(matcher, custom, optimizer, fm, templates, scene);
         // erased FeatureMap concept entry points
         const Size sz = getFeatureSize(fm);
-        if (sz.x != 960 || sz.y != 960) { std::printf("size %zu %zu\n", sz.x, sz.y); return 3; }
+        if (sz.x == 0 || sz.x != sz.y || sz.x != map.getFeatureSize().x) { std::printf("size %zu %zu\n", sz.x, sz.y); return 3; }
         const auto mm = minmaxTranslation(fm, templates[0], Point2{1.f, 0.f});
         if (!(mm[0] == mm[0])) { /* NaN: template not inside the map at 0 — fine, only the call matters */ }
         // clones outlive the originals
