@@ -98,6 +98,7 @@ typedef struct fdcm_search_stats {
 typedef struct fdcm_dt3 fdcm_dt3;               /* device feature map: [depth][height][pitch] fp32 planes */
 typedef struct fdcm_templates fdcm_templates;   /* device-resident template set */
 typedef struct fdcm_comm fdcm_comm;             /* multi-GPU communicator of one rank (one process per GPU, NCCL) */
+typedef struct fdcm_scene_batch fdcm_scene_batch;   /* double-buffered maps + build stream of a multi-scene batch */
 
 const char* fdcm_last_error(void);
 int32_t fdcm_abi_version(void);
@@ -209,6 +210,17 @@ fdcm_status fdcm_penalize(int32_t penalty_kind, float tau, fdcm_match* matches, 
 fdcm_status fdcm_sort_matches(fdcm_match* matches, int64_t n);
 /* getTemplateLengths without a device */
 fdcm_status fdcm_template_lengths(const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl, float* lengths);
+
+/* ---- multi-scene batches (BASELINE config 5: many scenes x one template set) ---------------------------------------
+ * What a caller of the reference writes as `for scene: fm = build_cpu_featuremap(scene); search(...); penalize; sort`
+ * (notebooks/pose_extimation_example.ipynb).  Scenes are CSR: scene_lines + scene_offsets[n_scenes + 1].  For every scene the
+ * batch builds its DT3 map and runs the fused search -> penalize -> top-k of `params->top_k` (> 0) records against the
+ * resident template set; two internal maps alternate so that the build of scene s+1 runs on a second stream under the
+ * search of scene s.  out: n_scenes x top_k records (scene-major), n_out[s] = records written for scene s. */
+fdcm_status fdcm_scene_batch_create(const fdcm_dt3_params* params, int32_t device, fdcm_scene_batch** out);
+fdcm_status fdcm_scene_batch_destroy(fdcm_scene_batch* batch);
+fdcm_status fdcm_search_scenes(fdcm_scene_batch* batch, const float* scene_lines, const int32_t* scene_offsets, int32_t n_scenes,
+                               const fdcm_templates* templates, const fdcm_search_params* params, fdcm_match* out, int32_t* n_out);
 
 /* ---- multi-GPU: one process per GPU, templates sharded by tmpl_idx, NCCL over NVLink ------------
  * The reference has no distributed code; these entry points are what a multi-GPU host (C++ or Python) calls instead of

@@ -21,7 +21,7 @@ from ._lib import MATCH_DTYPE, FdcmError, check, lib, ptr
 __all__ = [
     "distance", "Dt3CudaParameters", "Dt3Cuda", "build_cuda_featuremap", "ThreadPool", "DefaultSearch", "ConcentricRangeStrategy",
     "BatchOptimize", "DefaultOptimize", "DefaultMatch", "DefaultPenalty", "ExponentialPenalty", "Match",
-    "TemplateSet", "search", "search_topk", "penalize", "get_template_lengths", "sort_matches", "evaluate",
+    "TemplateSet", "SceneBatch", "search", "search_topk", "penalize", "get_template_lengths", "sort_matches", "evaluate",
     "minmax_translation", "get_feature_size", "establish_search_strategy", "optimize", "read", "write", "FdcmError", "MATCH_DTYPE",
 ]
 
@@ -340,6 +340,37 @@ def search_topk(featuremap, templates, scene, searcher, optimizer, penalty=None,
 def search_all(featuremap, templates, scene, searcher, optimizer, penalty=None, tmpl_idx_base=0):
     """Every match (hypothesis order) as a MATCH_DTYPE record array, optionally penalised on the device."""
     return _search_raw(featuremap, templates, scene, searcher, optimizer, penalty, 0, tmpl_idx_base).copy()
+
+
+class SceneBatch:
+    """Multi-scene batches (BASELINE config 5): per scene a DT3 build + fused search / penalty / top-k against one
+    resident TemplateSet, with the build of the next scene running under the search of the current one
+    (fdcm_search_scenes)."""
+
+    def __init__(self, params=None):
+        params = params or Dt3CudaParameters()
+        p = _lib.Dt3Params(params.depth, params.dt3_coeff, params.padding, int(params.distance))
+        h = C.c_void_p(0)
+        check(lib().fdcm_scene_batch_create(C.byref(p), params.device, C.byref(h)))
+        self._h, self.device = h, params.device
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib().fdcm_scene_batch_destroy(h)
+
+    def search_topk(self, scenes, templates, searcher, optimizer, penalty=None, k=10, tmpl_idx_base=0):
+        """-> list (one per scene) of MATCH_DTYPE arrays (ascending score)."""
+        tset = templates if isinstance(templates, TemplateSet) else TemplateSet(templates, self.device)
+        flat, off = _pack(scenes)
+        p = _lib.SearchParams(searcher.max_tmpl_lines, searcher.max_scene_lines, int(optimizer.batch_size),
+                              0 if penalty is None else penalty.kind, 0.0 if penalty is None else float(penalty.tau),
+                              int(k), int(tmpl_idx_base), 0, 0.0, 0.0, 0.0, 0.0)
+        n = len(off) - 1
+        out = np.zeros((max(n, 1), int(k)), MATCH_DTYPE)
+        cnt = np.zeros(max(n, 1), np.int32)
+        check(lib().fdcm_search_scenes(self._h, ptr(flat), ptr(off), n, tset._h, C.byref(p), ptr(out), ptr(cnt)))
+        return [out[i, : cnt[i]].copy() for i in range(n)]
 
 
 def penalize(penalty, matches, templatelengths):

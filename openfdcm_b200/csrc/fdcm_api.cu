@@ -1528,6 +1528,108 @@ extern "C" fdcm_status fdcm_comm_rebuild_broadcast(fdcm_comm* comm, fdcm_dt3* m,
     return st;
 }
 
+
+// =============================================================================================
+// multi-scene batches (BASELINE config 5): per scene a map build + a search of one resident template set
+// + fused penalty + top-k.  Two maps alternate: the build of scene s+1 is queued on a second stream before the host
+// blocks in the search of scene s, so the latency-bound build kernels run under the gather-bound search kernel.
+// =============================================================================================
+struct fdcm_scene_batch {
+    int device = 0;
+    fdcm_dt3_params params{};
+    fdcm_dt3* maps[2] = {nullptr, nullptr};
+    cudaStream_t build_stream = nullptr;
+    cudaEvent_t built[2] = {nullptr, nullptr};
+    ~fdcm_scene_batch() {
+        cudaSetDevice(device);
+        for (int i = 0; i < 2; ++i) {
+            if (maps[i]) fdcm_dt3_release(maps[i]);
+            if (built[i]) cudaEventDestroy(built[i]);
+        }
+        if (build_stream) cudaStreamDestroy(build_stream);
+    }
+};
+
+extern "C" fdcm_status fdcm_scene_batch_create(const fdcm_dt3_params* params, int32_t device, fdcm_scene_batch** out) {
+    if (!out) return fail(FDCM_ERR_INVALID, "out is null");
+    *out = nullptr;
+    if (fdcm_status st = validate_params(params)) return st;
+    CUDA_TRY(cudaSetDevice(device));
+    fdcm_scene_batch* b = new (std::nothrow) fdcm_scene_batch();
+    if (!b) return fail(FDCM_ERR_NOMEM, "host allocation failed");
+    b->device = device;
+    b->params = *params;
+    cudaError_t e = cudaStreamCreateWithFlags(&b->build_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&b->built[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        b->maps[i] = new (std::nothrow) fdcm_dt3();
+        if (!b->maps[i]) { delete b; return fail(FDCM_ERR_NOMEM, "host allocation failed"); }
+        b->maps[i]->params = *params;
+        b->maps[i]->device = device;
+        b->maps[i]->stage = 0;
+    }
+    if (e != cudaSuccess) {
+        delete b;
+        return fail(FDCM_ERR_CUDA, std::string("scene_batch_create: ") + cudaGetErrorString(e));
+    }
+    *out = b;
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_scene_batch_destroy(fdcm_scene_batch* b) {
+    delete b;
+    return FDCM_OK;
+}
+
+// queue the whole build of one scene on the batch's build stream
+static fdcm_status batch_queue_build(fdcm_scene_batch* b, int slot, const float* scene, int32_t n_lines) {
+    fdcm_dt3* m = b->maps[slot];
+    std::lock_guard<std::mutex> lk(m->search_mutex);
+    fdcm_status st = prepare_and_upload(m, scene, n_lines, b->build_stream);
+    if (st == FDCM_OK) st = run_build_kernels(m, b->build_stream);
+    if (st == FDCM_OK) st = upload_build_scene(m, scene, n_lines, b->build_stream);
+    if (st != FDCM_OK) {
+        const std::string msg = g_last_error;
+        cudaStreamSynchronize(b->build_stream);
+        invalidate_map(m);
+        g_last_error = msg;
+        return st;
+    }
+    CUDA_TRY(cudaEventRecord(b->built[slot], b->build_stream));
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_search_scenes(fdcm_scene_batch* b, const float* scene_lines, const int32_t* scene_offsets, int32_t n_scenes,
+                                          const fdcm_templates* templates, const fdcm_search_params* p, fdcm_match* out, int32_t* n_out) {
+    if (!b || !p || n_scenes < 0) return fail(FDCM_ERR_INVALID, "bad argument");
+    if (n_scenes == 0) return FDCM_OK;
+    if (!scene_offsets || !templates || !out || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
+    if (p->top_k <= 0) return fail(FDCM_ERR_INVALID, "fdcm_search_scenes needs top_k > 0 (fixed-size result per scene)");
+    for (int s = 0; s < n_scenes; ++s)
+        if (scene_offsets[s + 1] < scene_offsets[s]) return fail(FDCM_ERR_INVALID, "scene offsets must be non-decreasing");
+    if (scene_offsets[n_scenes] > 0 && !scene_lines) return fail(FDCM_ERR_INVALID, "scene_lines is null");
+    CUDA_TRY(cudaSetDevice(b->device));
+    cudaStream_t main_s;
+    if (fdcm_status st = get_stream(b->device, &main_s)) return st;
+    auto scene_ptr = [&](int s) { return scene_lines + 4 * (size_t)scene_offsets[s]; };
+    auto scene_n = [&](int s) { return scene_offsets[s + 1] - scene_offsets[s]; };
+    // the build stream must not overtake a search still running on the map it is about to overwrite: searches are
+    // host-synchronous, so every earlier search has completed when its slot comes round again
+    if (fdcm_status st = batch_queue_build(b, 0, scene_ptr(0), scene_n(0))) return st;
+    for (int s = 0; s < n_scenes; ++s) {
+        const int slot = s & 1;
+        if (s + 1 < n_scenes)
+            if (fdcm_status st = batch_queue_build(b, slot ^ 1, scene_ptr(s + 1), scene_n(s + 1))) return st;
+        CUDA_TRY(cudaStreamWaitEvent(main_s, b->built[slot], 0));
+        int64_t n = 0;
+        fdcm_search_params ps = *p;
+        const fdcm_status st = search_impl(b->maps[slot], templates, nullptr, FDCM_SCENE_RESIDENT, &ps, out + (size_t)s * p->top_k, p->top_k, &n, nullptr);
+        if (st != FDCM_OK) return st;
+        n_out[s] = (int32_t)n;
+    }
+    return FDCM_OK;
+}
+
 // optimize(optimizer, templates, alignments, featuremap) (matching/optimizestrategy.h:62-64;
 // batchoptimize.cpp:6-123 / defaultoptimize.cpp:6-93): the templates are taken as given (already aligned).
 extern "C" fdcm_status fdcm_optimize(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,

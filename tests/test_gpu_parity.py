@@ -528,3 +528,25 @@ def test_cpp_type_erased_strategies():
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "fused == generic == cloned" in r.stdout
+
+
+def test_scene_batch_pipelined_builds():
+    """fdcm_search_scenes: double-buffered maps, build(s+1) on a second stream under search(s); every scene's top-10 equals
+    the oracle's, including an empty scene in the middle and scenes of different map sizes."""
+    tmpls = synth_templates(30, 40, 640, seed=5100)
+    tset = fdcm.TemplateSet(tmpls)
+    scenes = [plant_instances(synth_scene(640, 480, 200, seed=5000 + s), tmpls, 640, 480, seed=5200 + s) for s in range(5)]
+    scenes.insert(2, np.zeros((4, 0), F32))
+    scenes.append(plant_instances(synth_scene(400, 300, 90, seed=5900), tmpls, 400, 300, seed=5901))
+    batch = fdcm.SceneBatch(fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    s_, o_, p_ = fdcm.DefaultSearch(4, 4), fdcm.BatchOptimize(10), fdcm.ExponentialPenalty(1.5)
+    for rep in range(2):          # the second pass reuses the two maps
+        got = batch.search_topk(scenes, tset, s_, o_, p_, k=10)
+        assert len(got) == len(scenes)
+        for i, scene in enumerate(scenes):
+            if scene.shape[1] == 0:
+                assert len(got[i]) == 0
+                continue
+            c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+            pen = orc.penalize(1, 1.5, c.search(tmpls, scene, 4, 4, batch=10), orc.template_lengths(tmpls))
+            assert np.array_equal(got[i], pen[np.lexsort((np.arange(len(pen)), pen["score"]))[:10]]), f"scene {i} (pass {rep})"
