@@ -228,26 +228,10 @@ def main():
         if comm is None:
             fdcm.check(L.fdcm_search_host(fm._h, h_lines.data_ptr(), h_off.data_ptr(), N_TMPL, None, fdcm._lib.FDCM_SCENE_RESIDENT,
                                           C.byref(p), fdcm.ptr(out), TOP_K, C.byref(n)))
-        else:   # host templates -> this rank's reusable device set, then the collective search
-            e2e_set.reload(h_lines, h_off)
-            fdcm.check(L.fdcm_comm_search_topk(comm._h, fm._h, e2e_set._h, None, fdcm._lib.FDCM_SCENE_RESIDENT, C.byref(p), fdcm.ptr(out),
-                                               TOP_K, C.byref(n)))
+        else:   # host templates of this rank's shard in, the merged global top-10 out
+            fdcm.check(L.fdcm_comm_search_host_topk(comm._h, fm._h, h_lines.data_ptr(), h_off.data_ptr(), N_TMPL, None,
+                                                    fdcm._lib.FDCM_SCENE_RESIDENT, C.byref(p), fdcm.ptr(out), TOP_K, C.byref(n)))
         return out[: n.value]
-
-    class _ReloadableSet:
-        """N > 1 e2e arm: re-upload the host templates every step (what fdcm_search_host does inside at N = 1)."""
-
-        def __init__(self):
-            self._h = C.c_void_p(0)
-
-        def reload(self, lines, offs):
-            if self._h:
-                L.fdcm_templates_release(self._h)
-            h = C.c_void_p(0)
-            fdcm.check(L.fdcm_templates_create(lines.data_ptr(), offs.data_ptr(), N_TMPL, local_rank, C.byref(h)))
-            self._h = h
-
-    e2e_set = _ReloadableSet()
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):

@@ -241,6 +241,10 @@ fdcm_status fdcm_comm_shard(int32_t n_items, int32_t rank, int32_t world, int32_
 fdcm_status fdcm_comm_search_topk(fdcm_comm* comm, const fdcm_dt3* map, const fdcm_templates* shard, const float* scene_xyxy,
                                   int32_t n_scene, const fdcm_search_params* params, fdcm_match* out, int64_t capacity,
                                   int64_t* n_out);
+/* the same with this rank's shard given as host templates (like fdcm_search_host: uploaded into a reusable device set) */
+fdcm_status fdcm_comm_search_host_topk(fdcm_comm* comm, const fdcm_dt3* map, const float* tmpl_lines, const int32_t* tmpl_offsets,
+                                       int32_t n_tmpl, const float* scene_xyxy, int32_t n_scene, const fdcm_search_params* params,
+                                       fdcm_match* out, int64_t capacity, int64_t* n_out);
 /* fdcm_dt3_rebuild on every rank with the kernels run on `root` only and the planes sent by ncclBroadcast (collective):
  * the alternative to every rank building the scene's map itself; bench.py measures both. */
 fdcm_status fdcm_comm_rebuild_broadcast(fdcm_comm* comm, fdcm_dt3* map, const float* scene_xyxy, int32_t n_lines, int32_t root);

@@ -91,6 +91,8 @@ SIGNATURES = {
     "fdcm_comm_info": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fdcm_comm_shard": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fdcm_comm_search_topk": (C.c_int, [_P, _P, _P, _P, C.c_int32, C.POINTER(SearchParams), _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "fdcm_comm_search_host_topk": (C.c_int, [_P, _P, _P, _P, C.c_int32, _P, C.c_int32, C.POINTER(SearchParams), _P, C.c_int64,
+                                             C.POINTER(C.c_int64)]),
     "fdcm_comm_rebuild_broadcast": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32]),
     "fdcm_set_host_threads": (C.c_int, [C.c_int32]),
     "fdcm_scene_batch_create": (C.c_int, [C.POINTER(Dt3Params), C.c_int32, C.POINTER(_P)]),

@@ -1699,12 +1699,13 @@ extern "C" fdcm_status fdcm_optimize(const fdcm_dt3* m, const float* tmpl_lines,
     return FDCM_OK;
 }
 
-extern "C" fdcm_status fdcm_search_host(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
-                                        const float* scene, int32_t n_scene, const fdcm_search_params* p, fdcm_match* out,
-                                        int64_t capacity, int64_t* n_out) {
+static fdcm_status search_host_impl(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                                    const float* scene, int32_t n_scene, const fdcm_search_params* p, fdcm_match* out,
+                                    int64_t capacity, int64_t* n_out, fdcm_comm* comm) {
     if (!m || !n_out) return fail(FDCM_ERR_INVALID, "null argument");
     *n_out = 0;
-    if (n_tmpl <= 0) return FDCM_OK;
+    if (n_tmpl < 0) return fail(FDCM_ERR_INVALID, "bad template count");
+    if (n_tmpl == 0 && !comm) return FDCM_OK;
     CUDA_TRY(cudaSetDevice(m->device));
     cudaStream_t s;
     if (fdcm_status st = get_stream(m->device, &s)) return st;
@@ -1714,8 +1715,23 @@ extern "C" fdcm_status fdcm_search_host(const fdcm_dt3* m, const float* tmpl_lin
         if (!m->host_tset) return fail(FDCM_ERR_NOMEM, "host allocation failed");
         m->host_tset->device = m->device;
     }
-    if (fdcm_status st = templates_load(m->host_tset, tmpl_lines, tmpl_offsets, n_tmpl, s)) return st;
-    return fdcm_search(m, m->host_tset, scene, n_scene, p, out, capacity, n_out);
+    static const int32_t zero_off[1] = {0};
+    if (fdcm_status st = templates_load(m->host_tset, tmpl_lines, n_tmpl ? tmpl_offsets : zero_off, n_tmpl, s)) return st;
+    return search_impl(m, m->host_tset, scene, n_scene, p, out, capacity, n_out, comm);
+}
+
+extern "C" fdcm_status fdcm_search_host(const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
+                                        const float* scene, int32_t n_scene, const fdcm_search_params* p, fdcm_match* out,
+                                        int64_t capacity, int64_t* n_out) {
+    return search_host_impl(m, tmpl_lines, tmpl_offsets, n_tmpl, scene, n_scene, p, out, capacity, n_out, nullptr);
+}
+
+// fdcm_comm_search_topk taking this rank's shard as host templates (uploaded into the map's reusable template set)
+extern "C" fdcm_status fdcm_comm_search_host_topk(fdcm_comm* comm, const fdcm_dt3* m, const float* tmpl_lines, const int32_t* tmpl_offsets,
+                                                  int32_t n_tmpl, const float* scene, int32_t n_scene, const fdcm_search_params* p,
+                                                  fdcm_match* out, int64_t capacity, int64_t* n_out) {
+    if (!comm) return fail(FDCM_ERR_INVALID, "comm is null");
+    return search_host_impl(m, tmpl_lines, tmpl_offsets, n_tmpl, scene, n_scene, p, out, capacity, n_out, comm);
 }
 
 extern "C" fdcm_status fdcm_search_last_hypotheses(const fdcm_dt3* m, int32_t* out, int64_t capacity, int64_t* n_out) {
