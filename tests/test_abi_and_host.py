@@ -158,9 +158,23 @@ def test_packio_read_write_roundtrip(tmp_path):
     assert fdcm.read(path).shape == (4, 0)
     with pytest.raises(RuntimeError):
         fdcm.read(str(tmp_path / "missing.scene"))
-    real = os.path.join(ROOT, "tests", "golden", "real_obj_01")
-    scene = fdcm.read(os.path.join(real, "camera_0.scene"))
+    real = os.path.join(ROOT, "tests", "golden", "real_assets", "obj_01")
+    scene = fdcm.read(os.path.join(real, "scene_0", "camera_0.scene"))
     assert scene.shape == (4, 557) and scene.dtype == np.float32
     assert 190 < scene.min() and scene.max() < 660
     tm = fdcm.read(os.path.join(real, "templates", "template_0.tmpl"))
     assert tm.shape[0] == 4 and 10 <= tm.shape[1] <= 40
+
+
+def test_every_real_asset_decodes():
+    """all 421 templates (12-33 lines) and 40 scenes (388-763 lines) of the reference's demo assets."""
+    import glob
+    real = os.path.join(ROOT, "tests", "golden", "real_assets")
+    tm = glob.glob(os.path.join(real, "obj_0*", "templates", "*.tmpl"))
+    sc = glob.glob(os.path.join(real, "obj_0*", "scene_*", "camera_0.scene"))
+    assert (len(tm), len(sc)) == (421, 40)
+    for p in tm:
+        assert 12 <= fdcm.read(p).shape[1] <= 33
+    for p in sc:
+        a = fdcm.read(p)
+        assert 388 <= a.shape[1] <= 763 and a.min() >= 0 and a.max() <= 800

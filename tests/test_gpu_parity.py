@@ -387,9 +387,9 @@ def test_real_asset_regression():
     notebooks/pose_extimation_example.ipynb: DefaultSearch(4,10), BatchOptimize(10), depth 30, coeff 5, padding 1.0, L2."""
     import glob
     import os
-    real = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_obj_01")
-    scene = fdcm.read(os.path.join(real, "camera_0.scene"))
-    tmpls = [fdcm.read(p) for p in sorted(glob.glob(os.path.join(real, "templates", "*.tmpl")))]
+    real = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "real_assets", "obj_01")
+    scene = fdcm.read(os.path.join(real, "scene_0", "camera_0.scene"))
+    tmpls = [fdcm.read(os.path.join(real, "templates", f"template_{i}.tmpl")) for i in range(24)]
     assert len(tmpls) == 24
     for padding in (1.0, 2.2):
         g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, padding))
