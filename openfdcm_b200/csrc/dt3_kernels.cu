@@ -114,30 +114,25 @@ __global__ void __launch_bounds__(256) raster_kernel(const float4* __restrict__ 
 }
 
 
-// general regime: materialise the {0, FLT_MAX} image (core/imgproc.h:174-175)
-__global__ void __launch_bounds__(256) mask_to_float_kernel(const uint32_t* __restrict__ mask, MapDims dm,
-                                                            float* __restrict__ planes) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)dm.D * dm.plane_elems;
-    if (i >= total) return;
-    const int x = (int)(i % dm.pitch);
-    const size_t row = i / dm.pitch;
-    const uint32_t w = mask[row * dm.wwords + (x >> 5)];
-    planes[i] = ((w >> (x & 31)) & 1u) ? 0.f : FLT_MAX;
-}
-
 // =============================================================================================
-// K2b: one literal Felzenszwalb pass (core/imgproc.h:91-130) per scan-line, one thread per scan-line.
-// Scan-line l of plane d starts at base + l*line_stride, element q at + q*elem_stride (rows:
-// line_stride = pitch, elem_stride = 1; columns: the other way round).  The envelope stack (v, z)
-// lives in a global workspace with the same indexing.  The second loop reproduces the reference's
-// in-place read of img(v_k, i): when v_k < q the value has already been overwritten.
-// kFromG: input is the u16 vertical distance of dt_col_exact_kernel (f = g*g, 0xFFFF -> FLT_MAX).
+// K2b: the literal Felzenszwalb pass (core/imgproc.h:91-130) for maps beyond the integer-exact regime (side > 2897),
+// where float(q^2) rounds and the reference's float arithmetic has to be replayed operation by operation.
+// One thread per COLUMN walks down its column: plane, envelope stack (v, z) and output accesses of a warp are
+// coalesced 128-byte rows.  The reference runs the same column pass twice with a transposition in between
+// (imgproc.h:186-190); so does this path (transpose_square_kernel), instead of a row pass whose lanes would sit a
+// whole pitch apart.  The second loop reproduces the reference's in-place read of img(v_k, i): when v_k < q the
+// value has already been overwritten.
+// kSrc: where the pass reads its input from
+//   kSrcPlane: the plane itself (second call)
+//   kSrcMask : the 1-bit edge mask, f = edge ? 0 : FLT_MAX (first call: the {0, FLT_MAX} image of imgproc.h:174-175 is
+//              never materialised)
+//   kSrcG16  : explicit u16 distances g, f = g * g, 0xFFFF -> FLT_MAX (fdcm_debug_dt_rows)
 // =============================================================================================
 struct EnvEntry { int v; float z; };
+enum { kSrcPlane = 0, kSrcMask = 1, kSrcG16 = 2 };
 
-template <bool kFromG>
-__global__ void __launch_bounds__(128) dt_pass_literal_kernel(const uint16_t* __restrict__ g, float* planes, MapDims dm,
+template <int kSrc>
+__global__ void __launch_bounds__(128) dt_pass_literal_kernel(const void* __restrict__ src, float* planes, MapDims dm,
                                                               EnvEntry* stack, int n, int n_lines, size_t elem_stride,
                                                               size_t line_stride) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
@@ -145,13 +140,17 @@ __global__ void __launch_bounds__(128) dt_pass_literal_kernel(const uint16_t* __
     if (l >= n_lines) return;
     const size_t base = (size_t)d * dm.plane_elems + (size_t)l * line_stride;
     float* out = planes + base;
-    const uint16_t* gin = g + base;
+    const uint16_t* gin = kSrc == kSrcG16 ? reinterpret_cast<const uint16_t*>(src) + base : nullptr;
+    // mask mode: scan line l is column l (elem_stride = pitch): bit (l & 31) of word (l >> 5) of every row
+    const uint32_t* mrow = kSrc == kSrcMask ? reinterpret_cast<const uint32_t*>(src) + (size_t)d * dm.H * dm.wwords + (l >> 5) : nullptr;
+    const uint32_t mbit = 1u << (l & 31);
     EnvEntry* st = stack + base;
     auto F = [&](int q) -> float {
-        if (kFromG) {
+        if (kSrc == kSrcG16) {
             const unsigned gv = gin[(size_t)q * elem_stride];
             return gv == kNoEdge16 ? FLT_MAX : (float)(gv * gv);
         }
+        if (kSrc == kSrcMask) return (mrow[(size_t)q * dm.wwords] & mbit) ? 0.f : FLT_MAX;
         return out[(size_t)q * elem_stride];
     };
     // first loop: lower envelope (imgproc.h:101-121); top of stack cached in registers
@@ -184,8 +183,34 @@ __global__ void __launch_bounds__(128) dt_pass_literal_kernel(const uint16_t* __
             znext = (k2 + 1 <= k) ? st[(size_t)(k2 + 1) * elem_stride].z : INFINITY;
         }
         const long long dq = (long long)q - v;
-        const float src = (kFromG && v >= q) ? F(v) : out[(size_t)v * elem_stride];
-        out[(size_t)q * elem_stride] = src + (float)(dq * dq);
+        const float srcv = (kSrc != kSrcPlane && v >= q) ? F(v) : out[(size_t)v * elem_stride];
+        out[(size_t)q * elem_stride] = srcv + (float)(dq * dq);
+    }
+}
+
+// in-place transposition of the square W x W region of every plane (img.transposeInPlace(), imgproc.h:187,189):
+// one CTA per pair of 32 x 32 tiles (i <= j), both staged through shared memory
+__global__ void __launch_bounds__(256) transpose_square_kernel(float* __restrict__ planes, MapDims dm, int ntiles) {
+    __shared__ float A[32][33], B[32][33];
+    // linear index of the pair (ti <= tj) in the upper triangle, row by row
+    int t = blockIdx.x, ti = 0;
+    while (t >= ntiles - ti) { t -= ntiles - ti; ++ti; }
+    const int tj = ti + t;
+    float* P = planes + (size_t)blockIdx.y * dm.plane_elems;
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;   // 32 x 8 threads
+    const int n = dm.W;
+    for (int r = ly; r < 32; r += 8) {
+        const int ya = ti * 32 + r, xa = tj * 32 + lx;        // tile (ti, tj): rows of ti, columns of tj
+        const int yb = tj * 32 + r, xb = ti * 32 + lx;        // tile (tj, ti)
+        A[r][lx] = (ya < n && xa < n) ? P[(size_t)ya * dm.pitch + xa] : 0.f;
+        B[r][lx] = (yb < n && xb < n) ? P[(size_t)yb * dm.pitch + xb] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ly; r < 32; r += 8) {
+        const int ya = ti * 32 + r, xa = tj * 32 + lx;
+        const int yb = tj * 32 + r, xb = ti * 32 + lx;
+        if (ya < n && xa < n) P[(size_t)ya * dm.pitch + xa] = B[lx][r];   // (ti, tj) <- transpose of (tj, ti)
+        if (ti != tj && yb < n && xb < n) P[(size_t)yb * dm.pitch + xb] = A[lx][r];
     }
 }
 
@@ -260,22 +285,26 @@ void launch_raster(const float* d_lines, const int32_t* d_bins, int n_lines, con
                                                                    dm, d_mask);
 }
 
-void launch_mask_to_float(const uint32_t* d_mask, const MapDims& dm, float* d_planes, cudaStream_t s) {
-    const size_t total = (size_t)dm.D * dm.plane_elems;
-    mask_to_float_kernel<<<cdiv(total, 256), 256, 0, s>>>(d_mask, dm, d_planes);
-}
-
-void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, float* d_planes, const MapDims& dm,
-                            void* d_stack, cudaStream_t s) {
+// src_kind: 0 = the plane itself, 1 = the edge mask, 2 = explicit u16 distances
+void launch_dt_pass_literal(int src_kind, bool along_rows, const void* d_src, float* d_planes, const MapDims& dm, void* d_stack,
+                            cudaStream_t s) {
     const int n = along_rows ? dm.W : dm.H;
     const int n_lines = along_rows ? dm.H : dm.W;
     const size_t es = along_rows ? 1 : (size_t)dm.pitch;
     const size_t ls = along_rows ? (size_t)dm.pitch : 1;
     dim3 grid(cdiv(n_lines, 128), dm.D);
-    if (from_g)
-        dt_pass_literal_kernel<true><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
+    if (src_kind == kSrcG16)
+        dt_pass_literal_kernel<kSrcG16><<<grid, 128, 0, s>>>(d_src, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
+    else if (src_kind == kSrcMask)
+        dt_pass_literal_kernel<kSrcMask><<<grid, 128, 0, s>>>(d_src, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
     else
-        dt_pass_literal_kernel<false><<<grid, 128, 0, s>>>(d_g, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
+        dt_pass_literal_kernel<kSrcPlane><<<grid, 128, 0, s>>>(d_src, d_planes, dm, (EnvEntry*)d_stack, n, n_lines, es, ls);
+}
+
+void launch_transpose_square(float* d_planes, const MapDims& dm, cudaStream_t s) {
+    const int nt = (dm.W + 31) / 32;
+    dim3 grid((unsigned)((size_t)nt * (nt + 1) / 2), dm.D);
+    transpose_square_kernel<<<grid, 256, 0, s>>>(d_planes, dm, nt);
 }
 
 void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s) {

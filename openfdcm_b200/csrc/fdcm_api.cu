@@ -586,17 +586,24 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
         }
     } else {
-        // side > 2897, L2 / L2^2: float(q^2) rounds, the reference's float arithmetic is replayed literally
+        // side > 2897, L2 / L2^2: float(q^2) rounds, the reference's float arithmetic is replayed literally.  Like the
+        // reference (imgproc.h:186-190): column pass, transpose, column pass, transpose -- every pass coalesced.
         {
-            KernelScope k("mask_to_float", N, s);
-            launch_mask_to_float(m->mask.as<uint32_t>(), dm, m->planes.as<float>(), s);
+            KernelScope k("dt_col_literal", (double)mask_bytes + N, s);
+            launch_dt_pass_literal(1, false, m->mask.p, m->planes.as<float>(), dm, m->stack.p, s);
         }
         {
-            KernelScope k("dt_col_literal", 2 * N, s);
-            launch_dt_pass_literal(false, false, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
+            KernelScope k("transpose", 2 * N, s);
+            launch_transpose_square(m->planes.as<float>(), dm, s);
         }
-        KernelScope k("dt_row_literal", 2 * N, s);
-        launch_dt_pass_literal(false, true, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
+        {
+            KernelScope k("dt_row_literal", 2 * N, s);
+            launch_dt_pass_literal(0, false, nullptr, m->planes.as<float>(), dm, m->stack.p, s);
+        }
+        {
+            KernelScope k("transpose", 2 * N, s);
+            launch_transpose_square(m->planes.as<float>(), dm, s);
+        }
     }
     const bool need_sqrt = dist == FDCM_L2;
     if (m->stage == 1) {
@@ -1832,7 +1839,7 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
             launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, 0, dm.H - 1, s);
             launch_dt_row_fill(dp.as<float>(), dm, ds.p, 0, dm.W - 1, s);
         } else {
-            launch_dt_pass_literal(true, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
+            launch_dt_pass_literal(2, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);
         }
     }
     if (e == cudaSuccess) e = cudaGetLastError();

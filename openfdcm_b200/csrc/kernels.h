@@ -9,9 +9,10 @@ namespace fdcm {
 
 // ---- dt3_kernels.cu ----
 void launch_raster(const float* d_lines, const int32_t* d_bins, int n_lines, const MapDims& dm, uint32_t* d_mask, cudaStream_t s);
-void launch_mask_to_float(const uint32_t* d_mask, const MapDims& dm, float* d_planes, cudaStream_t s);
-void launch_dt_pass_literal(bool from_g, bool along_rows, const uint16_t* d_g, float* d_planes, const MapDims& dm,
-                            void* d_stack, cudaStream_t s);
+// literal Felzenszwalb pass; src_kind: 0 = the plane itself, 1 = the 1-bit edge mask (column pass only), 2 = explicit u16 distances
+void launch_dt_pass_literal(int src_kind, bool along_rows, const void* d_src, float* d_planes, const MapDims& dm, void* d_stack,
+                            cudaStream_t s);
+void launch_transpose_square(float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_sqrt(float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, bool sqrt_first, cudaStream_t s);
 
