@@ -675,7 +675,7 @@ struct FPConfig {
 };
 
 // propagate phase shared by the fused kernels: thread t takes pixel q0 + t of image row y, reads its D values from the
-// tile (0xFFFFFFFF: FLT_MAX), runs the forward (ceil(1.5 D)) and backward (D + floor(1.5 D)) circular sweeps
+// tile (float bits written by the fill phase), runs the forward (ceil(1.5 D)) and backward (D + floor(1.5 D)) circular sweeps
 // P[c2] = min(P[c2], P[c1] + w_step) in registers and writes D coalesced row segments.
 template <int D>
 __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int chunk, int q0, int y, float* __restrict__ planes,
@@ -685,8 +685,7 @@ __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int ch
     float v[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        const uint32_t u = tile[(size_t)d * chunk + threadIdx.x];
-        v[d] = u == 0xFFFFFFFFu ? FLT_MAX : (float)u;
+        v[d] = __uint_as_float(tile[(size_t)d * chunk + threadIdx.x]);   // the fill phase stored float bits (FLT_MAX: no edge)
     }
     if (sqrt_first) {
 #pragma unroll
@@ -717,7 +716,7 @@ __global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
 dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
                          MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first) {
     using C = FPConfig<D>;
-    extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] squared distances (0xFFFFFFFF: FLT_MAX)
+    extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] squared distances as float bits (exact: < 2^24; FLT_MAX: no edge)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x;
     const int Hp = ((dm.H + 31) >> 5) << 5;                  // workspace rows per plane
@@ -743,9 +742,9 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const RowMeta* __r
             if (d < D) {
                 uint32_t* trow = fp_tile + (size_t)d * C::kChunk + lane;
                 if (Kp[p] > 0) {
-                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = rf[p].chunk(q0 + c, lane, le_mask);
+                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = __float_as_uint((float)rf[p].chunk(q0 + c, lane, le_mask));
                 } else {
-                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = 0xFFFFFFFFu;
+                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = __float_as_uint(FLT_MAX);
                 }
             }
         }
@@ -869,7 +868,10 @@ dt_l1_propagate_kernel(const uint2* __restrict__ info, float* __restrict__ plane
             const int d = warp + p * C::kWarps;
             if (d < D) {
                 uint32_t* trow = fp_tile + (size_t)d * C::kChunk + lane;
-                for (int c = 0; c < C::kChunk; c += 32) trow[c] = (q0 + c < dm.pitch) ? lf[p].chunk(q0 + c, lane) : 0xFFFFFFFFu;
+                for (int c = 0; c < C::kChunk; c += 32) {
+                    const uint32_t u = (q0 + c < dm.pitch) ? lf[p].chunk(q0 + c, lane) : 0xFFFFFFFFu;
+                    trow[c] = __float_as_uint(u == 0xFFFFFFFFu ? FLT_MAX : (float)u);
+                }
             }
         }
         __syncthreads();

@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(128, 6) search_warp_kernel(const __grid_consta
             {   // first window: 0 and the first batch of both directions when they fit into the warp
                 int lo, hi;
                 if (2 * span + 1 <= 32) { lo = max(minm, -span); hi = min(maxm, span); }
-                else if (span >= 16) { lo = 0; hi = min(maxm, span - 1); }           // 0 and most of the first batch upwards
+                else if (span >= 16) { lo = 0; hi = min(maxm, min(span, 31)); }     // 0 and the whole first batch upwards when it fits
                 else { lo = max(minm, -15); hi = min(maxm, 16); }
                 if (lo > 0) lo = 0;            // (limits always include 0: the template is inside the map at t = 0)
                 if (hi < 0) hi = 0;
