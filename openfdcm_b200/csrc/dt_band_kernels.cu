@@ -365,7 +365,7 @@ __host__ __device__ inline size_t band_alias_bytes(int pitch) {
 template <bool kFromG>
 __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict__ info, const uint16_t* __restrict__ g, MapDims dm,
                                                          int nbands, uint2* __restrict__ spill_all, int maxdepth,
-                                                         RowMeta* __restrict__ row_meta, int xsplit, int band_lo, int band_hi) {
+                                                         RowMeta* __restrict__ row_meta, int xsplit, int band_lo, int band_hi, int band_off) {
     extern __shared__ __align__(16) unsigned char band_smem[];
     __shared__ int s_kright[32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,8 +376,9 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
 
     // plane-fastest (neighbouring CTAs: different planes); the bands that overlap the scene's rows come first in the grid:
     // they carry the long serial chains
+    // band_off: first band (in that order) of this launch -- the scene bands and the far bands can be launched separately
     const int d = blockIdx.x % dm.D;
-    int b = blockIdx.x / dm.D;
+    int b = band_off + blockIdx.x / dm.D;
     {
         const int n_in = band_hi - band_lo + 1;
         b = b < n_in ? band_lo + b : (b - n_in < band_lo ? b - n_in : b);
@@ -714,11 +715,11 @@ __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int ch
 template <int D>
 __global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
 dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
-                         MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first) {
+                         MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first, int ya0, int na, int yb0) {
     using C = FPConfig<D>;
     extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] squared distances as float bits (exact: < 2^24; FLT_MAX: no edge)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int y = blockIdx.x;
+    const int y = (int)blockIdx.x < na ? ya0 + (int)blockIdx.x : yb0 + ((int)blockIdx.x - na);   // rows [ya0, ya0 + na) then [yb0, ...)
     const int Hp = ((dm.H + 31) >> 5) << 5;                  // workspace rows per plane
     RowFill rf[C::kPlanesPerWarp];
     int Kp[C::kPlanesPerWarp];
@@ -910,8 +911,9 @@ static RowWs row_ws(const MapDims& dm, void* d_ws, int win_lo, int win_hi) {
                  win_lo, win_hi - win_lo + 1};
 }
 
+// which: 0 = every band, 1 = only the bands that overlap the scene rows [row_lo, row_hi], 2 = only the others
 void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi,
-                            int row_lo, int row_hi, cudaStream_t s) {
+                            int row_lo, int row_hi, int which, cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     const int nbands = dt_band_count(dm);
     // split column: middle of the window that can hold edge pixels, on a 32-column boundary
@@ -919,15 +921,27 @@ void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDi
     int band_lo = (row_lo < 0 ? 0 : row_lo) >> 5, band_hi = (row_hi >= dm.H ? dm.H - 1 : row_hi) >> 5;
     if (band_hi < band_lo || band_hi >= nbands) { band_lo = 0; band_hi = nbands - 1; }
     const size_t smem = band_alias_bytes(dm.pitch) + (size_t)dm.wwords * sizeof(uint32_t);
+    const int n_in = band_hi - band_lo + 1;
+    const int band_off = which == 2 ? n_in : 0, n_sel = which == 0 ? nbands : (which == 1 ? n_in : nbands - n_in);
+    if (n_sel <= 0) return;
     if (d_g) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(dt_row_band_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dt_row_band_kernel<true><<<(unsigned)(dm.D * nbands), 64, smem, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
-                                                                             band_lo, band_hi);
+        dt_row_band_kernel<true><<<(unsigned)(dm.D * n_sel), 64, smem, s>>>(nullptr, d_g, dm, nbands, ws.spill, ws.maxdepth, ws.row_k, xsplit,
+                                                                            band_lo, band_hi, band_off);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(dt_row_band_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        dt_row_band_kernel<false><<<(unsigned)(dm.D * nbands), 64, smem, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
-                                                                              ws.spill, ws.maxdepth, ws.row_k, xsplit, band_lo, band_hi);
+        dt_row_band_kernel<false><<<(unsigned)(dm.D * n_sel), 64, smem, s>>>(reinterpret_cast<const uint2*>(d_info), nullptr, dm, nbands,
+                                                                             ws.spill, ws.maxdepth, ws.row_k, xsplit, band_lo, band_hi, band_off);
     }
+}
+
+// rows of the bands that overlap [row_lo, row_hi] (same clamping as launch_dt_row_envelope): [*y0, *y1)
+void dt_band_scene_rows(const MapDims& dm, int row_lo, int row_hi, int* y0, int* y1) {
+    const int nbands = dt_band_count(dm);
+    int band_lo = (row_lo < 0 ? 0 : row_lo) >> 5, band_hi = (row_hi >= dm.H ? dm.H - 1 : row_hi) >> 5;
+    if (band_hi < band_lo || band_hi >= nbands) { band_lo = 0; band_hi = nbands - 1; }
+    *y0 = band_lo * 32;
+    *y1 = min(dm.H, (band_hi + 1) * 32);
 }
 
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s) {
@@ -938,13 +952,17 @@ void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_
 
 bool dt_fill_propagate_supported(const MapDims& dm) { return dm.D == 30; }
 
+// rows [ya0, ya1) and [yb0, yb1) of the image (pass 0, H, 0, 0 for every row)
 void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,
-                              bool sqrt_first, cudaStream_t s) {
+                              bool sqrt_first, int ya0, int ya1, int yb0, int yb1, cudaStream_t s) {
     const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
     using C = FPConfig<30>;
     const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t);
+    const int na = max(0, ya1 - ya0), nb = max(0, yb1 - yb0);
+    if (na + nb <= 0) return;
     cudaFuncSetAttribute(dt_fill_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    dt_fill_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, ws.maxdepth, pp, sqrt_first ? 1 : 0);
+    dt_fill_propagate_kernel<30><<<na + nb, C::kThreads, smem, s>>>(ws.spill, ws.row_k, d_planes, dm, ws.maxdepth, pp, sqrt_first ? 1 : 0, ya0, na,
+                                                                    yb0);
 }
 
 void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& dm, cudaStream_t s) {

@@ -89,6 +89,20 @@ static fdcm_status get_copy_stream(int device, cudaStream_t* s) {
     return FDCM_OK;
 }
 
+// second stream of a device for kernels that run beside the main stream inside one build
+static std::map<int, cudaStream_t> g_aux_streams;
+static fdcm_status get_aux_stream(int device, cudaStream_t* s) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    auto o = g_aux_streams.find(device);
+    if (o == g_aux_streams.end()) {
+        cudaStream_t ns;
+        CUDA_TRY(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+        o = g_aux_streams.emplace(device, ns).first;
+    }
+    *s = o->second;
+    return FDCM_OK;
+}
+
 extern "C" fdcm_status fdcm_set_stream(int32_t device, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(g_mutex);
     if (cuda_stream) g_user_streams[device] = (cudaStream_t)cuda_stream;
@@ -225,6 +239,7 @@ struct fdcm_dt3 {
     const void* plan_planes = nullptr;
     int plan_tables_depth = -1;
     int n_sms = 148;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;   // fork / join of the second stream inside a build
     bool band_path = false, band_l1 = false;   // which distance-transform formulation this map uses (set by prepare)
     // search workspace (mutable state of the last search on this map)
     mutable std::mutex search_mutex;
@@ -254,6 +269,8 @@ struct fdcm_dt3 {
                           &s_perm, &s_sort_tmp})
             b->release();
         if (h_pinned) cudaFreeHost(h_pinned);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         if (h_scene_stage) cudaFreeHost(h_scene_stage);
         if (scene_stage_ev) cudaEventDestroy(scene_stage_ev);
         destroy_host_tset();
@@ -573,17 +590,53 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             KernelScope k("dt_col_band", (double)mask_bytes + (double)dt_band_info_bytes(dm), s);
             launch_dt_col_band(m->mask.as<uint32_t>(), dm, m->band_info.p, s);
         }
-        {
-            KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
-            launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, s);
-        }
         fused_propagate = m->stage != 1 && dt_fill_propagate_supported(dm);
-        if (fused_propagate) {
-            KernelScope k("dt_fill_propagate", N, s);
-            launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, s);
+        int ys0 = 0, ys1 = dm.H;                     // image rows of the bands that overlap the scene's rows
+        dt_band_scene_rows(dm, m->row_lo, m->row_hi, &ys0, &ys1);
+        const bool split = fused_propagate && (ys0 > 0 || ys1 < dm.H) && ys1 > ys0;
+        if (split) {
+            // The envelopes of the bands that hold the scene's edge rows are the long pole of the build (serial column chains,
+            // ~half of the issue slots idle); the rows of the other (far) bands only need the cheap far envelopes.  So the scene
+            // envelopes run on a second stream while the main stream fills + propagates the far rows under them.
+            cudaStream_t sa;
+            if (fdcm_status st = get_aux_stream(m->device, &sa)) return st;
+            if (!m->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+            if (!m->ev_join) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(m->ev_fork, s));
+            CUDA_TRY(cudaStreamWaitEvent(sa, m->ev_fork, 0));
+            {
+                KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), sa);
+                launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, 1, sa);
+            }
+            CUDA_TRY(cudaEventRecord(m->ev_join, sa));
+            {
+                KernelScope k("dt_row_envelope_far", (double)dt_band_info_bytes(dm), s);
+                launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, 2, s);
+            }
+            {
+                KernelScope k("dt_fill_propagate_far", N * (double)(dm.H - (ys1 - ys0)) / dm.H, s);
+                launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, 0, ys0, ys1,
+                                         dm.H, s);
+            }
+            CUDA_TRY(cudaStreamWaitEvent(s, m->ev_join, 0));
+            {
+                KernelScope k("dt_fill_propagate", N * (double)(ys1 - ys0) / dm.H, s);
+                launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, ys0, ys1, 0,
+                                         0, s);
+            }
         } else {
-            KernelScope k("dt_row_fill", N, s);
-            launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+            {
+                KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
+                launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, 0, s);
+            }
+            if (fused_propagate) {
+                KernelScope k("dt_fill_propagate", N, s);
+                launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, 0, dm.H, 0, 0,
+                                         s);
+            } else {
+                KernelScope k("dt_row_fill", N, s);
+                launch_dt_row_fill(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, s);
+            }
         }
     } else {
         // side > 2897, L2 / L2^2: float(q^2) rounds, the reference's float arithmetic is replayed literally.  Like the
@@ -1836,7 +1889,7 @@ extern "C" fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows
     if (e == cudaSuccess) {
         KernelScope k(literal == 2 ? "dt_row_band" : "dt_row_literal", 0.0, s);
         if (literal == 2) {
-            launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, 0, dm.H - 1, s);
+            launch_dt_row_envelope(nullptr, dg.as<uint16_t>(), dm, ds.p, 0, dm.W - 1, 0, dm.H - 1, 0, s);
             launch_dt_row_fill(dp.as<float>(), dm, ds.p, 0, dm.W - 1, s);
         } else {
             launch_dt_pass_literal(2, true, dg.as<uint16_t>(), dp.as<float>(), dm, ds.p, s);

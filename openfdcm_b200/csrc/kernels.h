@@ -38,13 +38,16 @@ size_t dt_band_spill_bytes(const MapDims& dm, int maxdepth);
 void launch_dt_col_band(const uint32_t* d_mask, const MapDims& dm, void* d_info, cudaStream_t s);
 // d_info (band records) or d_g (explicit u16 rows, tests) feeds the envelope build; exactly one of them is non-null
 // [row_lo, row_hi]: rows that can hold edge pixels (only used to order the bands in the grid)
+// which: 0 = every band, 1 = only the bands overlapping the scene rows [row_lo, row_hi], 2 = only the other (far) bands
 void launch_dt_row_envelope(const void* d_info, const uint16_t* d_g, const MapDims& dm, void* d_ws, int win_lo, int win_hi, int row_lo,
-                            int row_hi, cudaStream_t s);
+                            int row_hi, int which, cudaStream_t s);
+void dt_band_scene_rows(const MapDims& dm, int row_lo, int row_hi, int* y0, int* y1);
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
 // fill fused with propagateOrientation (and the L2 sqrt): the distance-transform planes never reach HBM
 bool dt_fill_propagate_supported(const MapDims& dm);
+// image rows [ya0, ya1) and [yb0, yb1)
 void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,
-                              bool sqrt_first, cudaStream_t s);
+                              bool sqrt_first, int ya0, int ya1, int yb0, int yb1, cudaStream_t s);
 
 // L1: row call straight from the band records (exact at any size), stand-alone or fused with propagateOrientation
 void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& dm, cudaStream_t s);
