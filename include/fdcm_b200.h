@@ -197,6 +197,11 @@ fdcm_status fdcm_concentric_search(const float* tmpl_xyxy, int32_t n_tmpl_lines,
  * out: n_rows x n floats (squared distances). */
 fdcm_status fdcm_debug_dt_rows(const uint16_t* g_rows, int32_t n_rows, int32_t n, int32_t literal, int32_t device, float* out);
 
+/* Parity hook: the fused fill + propagate kernel takes the square root of the L2 transform (core/imgproc.h:191-192) with
+ * rsqrt.approx + one Newton step instead of the general IEEE routine.  Its inputs are integers 0 .. 2^24 and FLT_MAX;
+ * this call compares the two on every one of them on the device.  n_mismatches must come back 0. */
+fdcm_status fdcm_debug_sqrt_check(int32_t device, int64_t* n_mismatches, uint32_t* first_mismatch);
+
 /* Orientation bins (closestOrientation, dt3cpu.h:93-114, for the `depth` keys of dt3cpu.h:188-190) of n lines,
  * computed on the host two ways: with libm atanf (what the reference does) and through the slope-threshold
  * table the device kernels use.  Host-only parity hook: the two outputs must be identical. */

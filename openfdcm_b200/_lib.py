@@ -73,6 +73,7 @@ SIGNATURES = {
     "fdcm_default_search": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32,
                                       C.POINTER(C.c_int32)]),
     "fdcm_debug_dt_rows": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "fdcm_debug_sqrt_check": (C.c_int, [C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_uint32)]),
     "fdcm_concentric_search": (C.c_int, [_P, C.c_int32, _P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
                                          C.c_float, _P, C.c_int32, C.POINTER(C.c_int32)]),
     "fdcm_orientation_bins": (C.c_int, [C.c_int32, _P, C.c_int32, _P, _P]),

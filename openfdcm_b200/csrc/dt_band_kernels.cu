@@ -675,6 +675,46 @@ struct FPConfig {
     static constexpr int kChunk = kThreads;             // pixels per iteration = one per thread in the propagate phase
 };
 
+// sqrtf for the values the fill phase produces: integers 0 .. 2^24 (exactly representable squared distances) and FLT_MAX
+// (no edge in the plane).  rsqrt.approx + one Newton step carried out with two fused multiply-adds is correctly rounded
+// for every one of them (fdcm_debug_sqrt_check compares all 2^24 + 2 inputs with the IEEE sqrtf on the device;
+// tests/test_gpu_parity.py::test_fast_sqrt_is_exact); 6 instructions instead of the ~10 of the general routine, which
+// also has to handle subnormals and non-integers.  0 * inf = NaN for the input 0 is mapped back by the final max.
+__device__ __forceinline__ float sqrt_exact_int(float n) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(n));
+    const float s = __fmul_rn(n, r);
+    const float h = __fmul_rn(0.5f, r);
+    const float e = __fmaf_rn(-s, s, n);
+    return fmaxf(__fmaf_rn(e, h, s), 0.f);
+}
+
+__global__ void sqrt_check_kernel(unsigned long long* __restrict__ n_bad, uint32_t* __restrict__ first_bad) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;       // 0 .. 2^24 + 1
+    float x = (float)i;
+    if (i == (1u << 24) + 1u) x = FLT_MAX;
+    if (i > (1u << 24) + 1u) return;
+    if (__float_as_uint(sqrt_exact_int(x)) != __float_as_uint(sqrtf(x))) {
+        if (atomicAdd(n_bad, 1ull) == 0ull) *first_bad = i;
+    }
+}
+
+// number of inputs (integers 0 .. 2^24 and FLT_MAX) on which sqrt_exact_int differs from the IEEE sqrtf
+cudaError_t run_sqrt_check(unsigned long long* h_bad, uint32_t* h_first, cudaStream_t s) {
+    unsigned long long* d_bad = nullptr;
+    cudaError_t e = cudaMalloc(&d_bad, 16);
+    if (e != cudaSuccess) return e;
+    cudaMemsetAsync(d_bad, 0, 16, s);
+    sqrt_check_kernel<<<((1u << 24) + 2u + 255u) / 256u, 256, 0, s>>>(d_bad, reinterpret_cast<uint32_t*>(d_bad + 1));
+    unsigned long long h[2] = {0, 0};
+    e = cudaMemcpyAsync(h, d_bad, 16, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d_bad);
+    *h_bad = h[0];
+    *h_first = (uint32_t)h[1];
+    return e;
+}
+
 // propagate phase shared by the fused kernels: thread t takes pixel q0 + t of image row y, reads its D values from the
 // tile (float bits written by the fill phase), runs the forward (ceil(1.5 D)) and backward (D + floor(1.5 D)) circular sweeps
 // P[c2] = min(P[c2], P[c1] + w_step) in registers and writes D coalesced row segments.
@@ -690,7 +730,7 @@ __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int ch
     }
     if (sqrt_first) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) v[d] = sqrtf(v[d]);
+        for (int d = 0; d < D; ++d) v[d] = sqrt_exact_int(v[d]);
     }
     constexpr int fwd = (3 * D + 1) / 2;
     constexpr int bwd = D + (3 * D) / 2;

@@ -392,48 +392,45 @@ static fdcm_status build_integral_plan(fdcm_dt3* m, cudaStream_t s) {
     m->plan_W = -1;
     const int rlen = std::max(dm.W, dm.H);
     std::vector<int32_t> rtab((size_t)dm.D * rlen);
-    struct Item { double work; int2 it; };
+    struct Item { int work; int4 it; };
     std::vector<Item> items;
-    const int CW = integral_strip_chains();
+    const int CW = integral_strip_chains(), RB = integral_tile_steps();
     for (int d = 0; d < dm.D; ++d) {
         const int mode = m->integ.mode[d];
         const float r = mode == 1 ? m->integ.ry[d] : m->integ.rx[d];
         int32_t* R = rtab.data() + (size_t)d * rlen;
         for (int i = 0; i < rlen; ++i) R[i] = (int32_t)(long long)std::round((float)i * r);
         if (mode != 1 && mode != 2) continue;
+#ifdef FDCM_AB_ONLY_MODE
+        if (mode != FDCM_AB_ONLY_MODE) continue;
+#endif
         const int n_major = mode == 1 ? dm.W : dm.H, n_minor = mode == 1 ? dm.H : dm.W;
         const int Rend = R[n_major - 1];
         const int cmin = Rend > 0 ? -Rend : 0, cmax = (Rend < 0 ? -Rend : 0) + n_minor - 1;
+        const int nblk = (n_major + RB - 1) / RB;
         for (int c0 = cmin; c0 <= cmax; c0 += CW) {
-            // steps at which the middle chain of the strip lies inside the image (R is monotone): the strip's work
-            const int cm = std::min(c0 + CW / 2, cmax);
-            int lo = 0, hi = n_major;   // count i with 0 <= cm + R(i) < n_minor
-            int cnt = 0;
-            if (Rend == 0) cnt = (cm >= 0 && cm < n_minor) ? n_major : 0;
-            else {
-                auto first_ge = [&](int v) {   // first i with sgn * R(i) >= v for the monotone direction
-                    int a = lo, b = hi;
-                    while (a < b) { const int mid = (a + b) / 2; if ((Rend > 0 ? R[mid] : -R[mid]) >= v) b = mid; else a = mid + 1; }
-                    return a;
-                };
-                if (Rend > 0) cnt = first_ge(n_minor - cm) - first_ge(-cm);          // -cm <= R < n_minor - cm
-                else cnt = first_ge(cm + 1) - first_ge(cm - n_minor + 1);            // cm - n_minor < -R <= cm
+            // tiles in which some chain of the strip lies inside the image (R is monotone: they form one range)
+            int b_lo = nblk, b_hi = 0;
+            for (int b = 0; b < nblk; ++b) {
+                const int i0 = b * RB, i1 = std::min(n_major, i0 + RB);
+                const int rlo = std::min(R[i0], R[i1 - 1]), rhi = std::max(R[i0], R[i1 - 1]);
+                if (c0 + CW - 1 + rhi >= 0 && c0 + rlo <= n_minor - 1) { b_lo = std::min(b_lo, b); b_hi = std::max(b_hi, b + 1); }
             }
-            items.push_back(Item{(double)std::max(cnt, 1), make_int2(d, c0)});
+            if (b_lo < b_hi) items.push_back(Item{b_hi - b_lo, make_int4(d, c0, b_lo, b_hi)});
         }
     }
     std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.work > b.work; });
-    std::vector<int2> flat(items.size());
+    std::vector<int4> flat(items.size());
     for (size_t i = 0; i < items.size(); ++i) flat[i] = items[i].it;
     CUDA_TRY(m->rtab.reserve(rtab.size() * sizeof(int32_t)));
-    CUDA_TRY(m->integ_items.reserve(std::max<size_t>(8, flat.size() * sizeof(int2))));
+    CUDA_TRY(m->integ_items.reserve(std::max<size_t>(16, flat.size() * sizeof(int4))));
     CUDA_TRY(cudaMemcpyAsync(m->rtab.p, rtab.data(), rtab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(m->integ_items.p, flat.data(), flat.size() * sizeof(int2), cudaMemcpyHostToDevice, s));
+    if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(m->integ_items.p, flat.data(), flat.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaStreamSynchronize(s));   // the host vectors go out of scope (rare: only when the geometry changes)
     IntegralPlanDev& pl = m->integ_plan;
     pl.rtab = m->rtab.as<int32_t>();
     pl.rlen = rlen;
-    pl.items = m->integ_items.as<int2>();
+    pl.items4 = m->integ_items.as<int4>();
     pl.n_items = (int)flat.size();
     if (!integral_tma_encode(m->planes.p, dm, &pl.map_y, &pl.map_x))
         return fail(FDCM_ERR_CUDA, "cuTensorMapEncodeTiled failed for the feature-map planes");
@@ -1868,6 +1865,19 @@ extern "C" fdcm_status fdcm_concentric_search(const float* tmpl, int32_t L, cons
         out_pairs[2 * i] = pairs[2 * (size_t)i];
         out_pairs[2 * i + 1] = subset[(size_t)pairs[2 * (size_t)i + 1]];
     }
+    return FDCM_OK;
+}
+
+extern "C" fdcm_status fdcm_debug_sqrt_check(int32_t device, int64_t* n_mismatches, uint32_t* first_mismatch) {
+    if (!n_mismatches || !first_mismatch) return fail(FDCM_ERR_INVALID, "null output");
+    CUDA_TRY(cudaSetDevice(device));
+    cudaStream_t s;
+    if (fdcm_status st = get_stream(device, &s)) return st;
+    unsigned long long bad = 0;
+    uint32_t first = 0;
+    CUDA_TRY(run_sqrt_check(&bad, &first, s));
+    *n_mismatches = (int64_t)bad;
+    *first_mismatch = first;
     return FDCM_OK;
 }
 

@@ -20,13 +20,14 @@ void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, 
 struct IntegralPlanDev {
     const int32_t* rtab;         // [D][rlen] cumulative minor-axis shift R(i) = (long)roundf(i * r) per plane
     int rlen;
-    const int2* items;           // (plane, first chain of the strip), heaviest first
+    const int4* items4;          // (plane, first chain of the strip, first tile, end tile: where the strip meets the image), heaviest first
     int n_items;
     int* counter;                // work counter, zero before the launch
     CUtensorMap map_y, map_x;    // the planes with the y-major / x-major box shapes
 };
 size_t integral_tma_smem_bytes();
 int integral_strip_chains();
+int integral_tile_steps();
 bool integral_tma_encode(const void* planes, const MapDims& dm, CUtensorMap* map_y, CUtensorMap* map_x);
 void launch_integral_tma(float* d_planes, const MapDims& dm, const IntegralParams& ip, const IntegralPlanDev& plan, int n_sms,
                          cudaStream_t s);
@@ -53,6 +54,8 @@ void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, in
 void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& dm, cudaStream_t s);
 void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& dm, const PropParams& pp, cudaStream_t s);
 size_t dt_band_smem_bytes(const MapDims& dm);
+// parity hook of the fused fill's square root (integers 0 .. 2^24 and FLT_MAX against the IEEE sqrtf)
+cudaError_t run_sqrt_check(unsigned long long* h_bad, uint32_t* h_first, cudaStream_t s);
 
 // ---- search_kernels.cu ----
 struct MapView {                 // read-only view of a built feature map

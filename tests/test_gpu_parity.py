@@ -40,6 +40,27 @@ def test_build_stages_small(dist, stage):
     _assert_planes(g, c, f"{dist} stage {stage}")
 
 
+@pytest.mark.parametrize("geom", [(320, 240, 1.5), (333, 517, 1.0), (1201, 130, 1.2)], ids=lambda g: f"{g[0]}x{g[1]}")
+def test_line_integral_geometries(geom):
+    """lineIntegral against the oracle on map sides that are / are not multiples of 4 and 32: strips that leave the image
+    on either side, tile ranges clipped to the image."""
+    w, h, pad = geom
+    scene = synth_scene(w, h, 80, seed=w + h)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, pad, fdcm.distance.L2))
+    c = orc.Dt3Cpu(scene, 30, 5.0, pad, orc.L2)
+    _assert_planes(g, c, f"integral {w}x{h}")
+
+
+def test_fast_sqrt_is_exact():
+    """The fused fill's rsqrt + Newton square root equals the IEEE sqrtf on every input it can see: all integers
+    0 .. 2^24 (squared distances of the exact regime) and FLT_MAX (planes without edges)."""
+    import ctypes as C
+    from openfdcm_b200._lib import check, lib
+    bad, first = C.c_int64(-1), C.c_uint32(0)
+    check(lib().fdcm_debug_sqrt_check(0, C.byref(bad), C.byref(first)))
+    assert bad.value == 0, f"{bad.value} mismatches, first at input {first.value}"
+
+
 def test_edge_masks_and_bins_bit_exact():
     scene = synth_scene(640, 480, 300, seed=1000)
     g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5, fdcm.distance.L2_SQUARED), stage=1)
