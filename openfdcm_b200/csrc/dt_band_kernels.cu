@@ -520,6 +520,19 @@ struct RowFill {
             cur = lo;
         }
     }
+    // kResolvedBelow: the entries before the previous batch have already been replaced by their resolved form {base,
+    // v | first pixel << 16} (the fused kernel's resolve pass writes every batch back before it moves on)
+    __device__ uint32_t slow_base_resolved(int v) const {
+        int lo = 0, hi = e0 - 33;                // largest o <= e0 - 33 with first pixel <= v (entry 0 starts at pixel 0)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if ((int)(row[mid < KL ? mid : mid + roff].y >> 16) <= v) lo = mid; else hi = mid - 1;
+        }
+        const uint2 e = row[lo < KL ? lo : lo + roff];
+        const int dd = v - (int)(e.y & 0xFFFFu);
+        return e.x + (uint32_t)(dd * dd);
+    }
+    template <bool kResolvedBelow = false>
     __device__ __forceinline__ void resolve(int lane) {
         const int bv = (int)(be.y & 0xFFFFu), bs = (int)(be.y >> 16);
         uint32_t base = be.x - (uint32_t)(bv * bv);
@@ -550,7 +563,7 @@ struct RowFill {
             }
             bool ready = !chain;
             if (chain && !found) {               // owner further than 32 entries below: walk the global array
-                base = slow_base(e0 + lane);
+                base = kResolvedBelow ? slow_base_resolved(bv) : slow_base(e0 + lane);
                 ready = true;
             }
             const int src = owner & 31;
@@ -626,6 +639,75 @@ struct RowFill {
         }
         const int dq = q0 + lane - ov;
         return ob + (uint32_t)(dq * dq);
+    }
+
+    // ---- batch-driven fill (fused kernel): lane = envelope entry ----
+    // Inside the scene's rows most envelope entries own one to four pixels (every edge pixel of a line that runs along the
+    // row is a site of its own), so walking the pixels and looking the owners up pays the bookkeeping per 32 pixels many
+    // times per batch of entries.  Here every lane takes one entry of a batch of 32 and writes the entry's first kHead
+    // pixels itself; the entries that own more are then taken one at a time by the whole warp (lane = pixel).
+    // The fused kernel first runs a resolve pass (warp = plane, batches in order, previous batch in registers): it turns
+    // every entry into {base, v | first pixel << 16} and writes it back in place.  After that a batch is a self-contained
+    // unit of work, and the batches of all planes are dealt to the warps: a plane with a thousand entries in this row no
+    // longer holds one warp back while the others wait at the barrier.
+    int bend;               // first pixel of the entry that follows the batch (uniform); 0xFFFF: none
+    // resolve pass (sequential over the batches of one plane's row): write the current batch back in resolved form
+    __device__ __forceinline__ void write_back(int lane) const {
+        const int i = e0 + lane;
+        if (i < K) const_cast<uint2*>(row)[i < KL ? i : i + roff] = be;
+    }
+    // (the pass does little per batch, so it runs at the latency of its loads: three batches are kept in flight; a batch
+    // is written back only after its successors were loaded, so everything this function converts is still raw)
+    __device__ __forceinline__ void advance_resolved(int lane, uint2& nbe2, uint2& nbe3) {
+        e0 += 32;
+        pbe = be;
+        const uint32_t prev_last = raw_last;
+        raw_last = __shfl_sync(0xffffffffu, nbe.y >> 16, 31);
+        be = convert(nbe, e0 + lane, lane, prev_last);
+        nbe = nbe2;
+        nbe2 = nbe3;
+        nbe3 = load_raw(e0 + 96 + lane);
+        resolve<true>(lane);
+    }
+    // a batch of the resolved array as a unit of the fill
+    __device__ __forceinline__ void load_unit(const uint2* row_entries, int kl, int k, int roff_, int j, int bend_, int lane) {
+        row = row_entries;
+        KL = kl; K = k; roff = roff_;
+        e0 = 32 * j;
+        bend = bend_;
+        be = load_raw(e0 + lane);
+    }
+    static constexpr int kHead = 4;
+    // writes the pixels of the batch inside [q0, q1) into trow (the tile row of this plane, pixel q0 at trow[0]) as float
+    // bits of the (exact) squared distances
+    __device__ __forceinline__ void write_unit(int q0, int q1, uint32_t* __restrict__ trow, int lane) const {
+        const int s = (int)(be.y >> 16);                          // (sentinel lanes past the last entry: 0xFFFF, own nothing)
+        int send = __shfl_down_sync(0xffffffffu, s, 1);           // the next entry's first pixel ends this entry's interval
+        if (lane == 31) send = bend;
+        const int a = max(s, q0), b = min(send, q1);
+        const int len = b - a;
+        const int v = (int)(be.y & 0xFFFFu);
+        const uint32_t base = be.x;
+        uint32_t* tp = trow + (a - q0);
+#pragma unroll
+        for (int t = 0; t < kHead; ++t) {
+            if (t < len) {
+                const int dq = a + t - v;
+                tp[t] = __float_as_uint((float)(base + (uint32_t)(dq * dq)));
+            }
+        }
+        unsigned lng = __ballot_sync(0xffffffffu, len > kHead);
+        while (lng) {
+            const int e = __ffs(lng) - 1;
+            lng &= lng - 1u;
+            const int ae = __shfl_sync(0xffffffffu, a, e) + kHead, bb = __shfl_sync(0xffffffffu, b, e);
+            const int ve = __shfl_sync(0xffffffffu, v, e);
+            const uint32_t base_e = __shfl_sync(0xffffffffu, base, e);
+            uint32_t* tq = trow + (ae + lane - q0);
+            int dq = ae + lane - ve;
+#pragma unroll 1                                                  // (typically one or two rounds: an unrolled body with its remainder code costs more)
+            for (int n = bb - ae - lane; n > 0; n -= 32, dq += 32, tq += 32) *tq = __float_as_uint((float)(base_e + (uint32_t)(dq * dq)));
+        }
     }
 };
 
@@ -752,45 +834,122 @@ __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int ch
     for (int d = 0; d < D; ++d) op[(size_t)d * dm.plane_elems] = v[d];
 }
 
+constexpr int kFPMaxBatches = 96;        // envelope entries per row <= window width <= 2897 -> at most 91 batches of 32
+constexpr int kFPMaxChunks = 8;
+
 template <int D>
 __global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
-dt_fill_propagate_kernel(const uint2* __restrict__ spill_all, const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
+dt_fill_propagate_kernel(uint2* spill_all /* rewritten in place by the resolve pass: no __restrict__, coherent loads */,
+                         const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
                          MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first, int ya0, int na, int yb0) {
     using C = FPConfig<D>;
     extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] squared distances as float bits (exact: < 2^24; FLT_MAX: no edge)
+    __shared__ uint16_t s_first[D][kFPMaxBatches + 1];       // first pixel of every batch of every plane's envelope (then 0xFFFF)
+    __shared__ int4 s_meta[D];                               // {k_left, entries, array offset of the right entries, first right pixel}
+    __shared__ uint16_t s_pref[kFPMaxChunks][32];            // per chunk: units of the planes before plane d ([D]: all units)
+    __shared__ uint8_t s_jl[kFPMaxChunks][32];               // per chunk: first batch of plane d that reaches into the chunk
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = (int)blockIdx.x < na ? ya0 + (int)blockIdx.x : yb0 + ((int)blockIdx.x - na);   // rows [ya0, ya0 + na) then [yb0, ...)
     const int Hp = ((dm.H + 31) >> 5) << 5;                  // workspace rows per plane
-    RowFill rf[C::kPlanesPerWarp];
-    int Kp[C::kPlanesPerWarp];
+    const int nchunks = (dm.W + C::kChunk - 1) / C::kChunk;
+
+    // ---- resolve pass (warp w: planes w and w + kWarps): resolved entries back in place, first pixel of every batch ----
 #pragma unroll
     for (int p = 0; p < C::kPlanesPerWarp; ++p) {
-        const int d = warp + p * C::kWarps;   // planes half a turn apart: envelope sizes peak near the horizontal planes
-        Kp[p] = 0;
+        const int d = warp + p * C::kWarps;
         if (d < D) {
             const size_t prow = (size_t)d * Hp + y;
             const RowMeta meta = row_meta[prow];
-            Kp[p] = meta.k_left + meta.k_right;
-            rf[p].init(spill_all + prow * maxdepth, meta, maxdepth, lane);
+            const int K = meta.k_left + meta.k_right;
+            if (lane == 0) s_meta[d] = make_int4(meta.k_left, K, maxdepth - K, meta.right_start);
+            const int nb = (K + 31) >> 5;
+            for (int j = nb + lane; j <= kFPMaxBatches; j += 32) s_first[d][j] = 0xFFFF;
+            if (K > 0) {
+                RowFill rf;
+                rf.init(spill_all + prow * maxdepth, meta, maxdepth, lane);
+                uint2 nbe2 = rf.load_raw(64 + lane), nbe3 = rf.load_raw(96 + lane);
+                for (;;) {
+                    rf.write_back(lane);
+                    __syncwarp();                                // (later batches may look entries of this one up: slow_base_resolved)
+                    if (lane == 0) s_first[d][rf.e0 >> 5] = (uint16_t)(rf.be.y >> 16);
+                    if (rf.e0 + 32 >= K) break;
+                    rf.advance_resolved(lane, nbe2, nbe3);
+                }
+            }
         }
     }
-    const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
-    for (int q0 = 0; q0 < dm.W; q0 += C::kChunk) {
-        // ---- fill ----
+    __syncthreads();
+    // ---- units per chunk (warp c: chunk c, lane = plane): batches jl .. jh reach into [q0, q1) ----
+    if (warp < nchunks && warp < kFPMaxChunks) {
+        const int q0 = warp * C::kChunk, q1 = q0 + C::kChunk;
+        int n = 0, jl = 0;
+        if (lane < D) {
+            const int nb = (s_meta[lane].y + 31) >> 5;
+            if (nb > 0) {
+                int lo = 0, hi = nb - 1;                     // smallest j with first[j + 1] > q0 (first[nb] = 0xFFFF)
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if ((int)s_first[lane][mid + 1] > q0) hi = mid; else lo = mid + 1; }
+                jl = lo;
+                lo = jl; hi = nb - 1;                        // largest j with first[j] < q1 (first[jl] < q1: rows start at pixel 0)
+                while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if ((int)s_first[lane][mid] < q1) lo = mid; else hi = mid - 1; }
+                n = (int)s_first[lane][jl] < q1 ? lo - jl + 1 : 0;
+            }
+        }
+        int pre = n;                                         // inclusive prefix sum over the planes
 #pragma unroll
-        for (int p = 0; p < C::kPlanesPerWarp; ++p) {
-            const int d = warp + p * C::kWarps;
-            if (d < D) {
-                uint32_t* trow = fp_tile + (size_t)d * C::kChunk + lane;
-                if (Kp[p] > 0) {
-                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = __float_as_uint((float)rf[p].chunk(q0 + c, lane, le_mask));
-                } else {
-                    for (int c = 0; c < C::kChunk; c += 32) trow[c] = __float_as_uint(FLT_MAX);
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, pre, o); if (lane >= o) pre += t; }
+        s_pref[warp][lane] = (uint16_t)(pre - n);            // lanes >= D carry the total
+        s_jl[warp][lane] = (uint8_t)jl;
+    }
+    __syncthreads();
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int q0 = ch * C::kChunk;
+        // ---- fill: the batches that reach into the chunk, dealt round-robin to the warps ----
+        {
+            const int pref = s_pref[ch][lane], jl = s_jl[ch][lane];     // lane = plane
+            const int n_units = __shfl_sync(0xffffffffu, pref, D);
+#ifdef FDCM_AB_SKIP_FILL
+            if (dm.W < 0)
+#endif
+            {
+                // (the entries of the next unit are loaded before the current one is written: the L2 round trip of a unit
+                // hides behind the pixel stores of its predecessor)
+                auto load = [&](int u, RowFill& rf) -> int {
+                    const unsigned le = __ballot_sync(0xffffffffu, lane < D && pref <= u);
+                    const int d = 31 - __clz(le);            // the last plane whose units start at or before u
+                    const int j = __shfl_sync(0xffffffffu, jl, d) + u - __shfl_sync(0xffffffffu, pref, d);
+                    const int4 m = s_meta[d];
+                    rf.load_unit(spill_all + ((size_t)d * Hp + y) * maxdepth, m.x, m.y, m.z, j, (int)s_first[d][j + 1], lane);
+                    return d;
+                };
+                RowFill cur, nxt;
+                int u = warp, d_cur = 0, d_nxt = 0;
+                if (u < n_units) d_cur = load(u, cur);
+                while (u < n_units) {
+                    const int u2 = u + C::kWarps;
+                    if (u2 < n_units) d_nxt = load(u2, nxt);
+                    cur.write_unit(q0, q0 + C::kChunk, fp_tile + (size_t)d_cur * C::kChunk, lane);
+                    cur.be = nxt.be;
+                    cur.bend = nxt.bend;
+                    d_cur = d_nxt;
+                    u = u2;
+                }
+            }
+            // planes without an edge pixel: FLT_MAX stays (imgproc.h:174)
+#pragma unroll
+            for (int p = 0; p < C::kPlanesPerWarp; ++p) {
+                const int d = warp + p * C::kWarps;
+                if (d < D && s_meta[d].y == 0) {
+                    uint32_t* trow = fp_tile + (size_t)d * C::kChunk;
+                    for (int c = lane; c < C::kChunk; c += 32) trow[c] = __float_as_uint(FLT_MAX);
                 }
             }
         }
         __syncthreads();
         // ---- propagate: one pixel per thread ----
+#ifdef FDCM_AB_SKIP_PROP
+        if (dm.W < 0)
+#endif
         propagate_from_tile<D>(fp_tile, C::kChunk, q0, y, planes, dm, pp, sqrt_first);
         __syncthreads();
     }
