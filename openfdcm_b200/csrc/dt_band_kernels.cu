@@ -641,11 +641,10 @@ struct RowFill {
         return ob + (uint32_t)(dq * dq);
     }
 
-    // ---- batch-driven fill (fused kernel): lane = envelope entry ----
+    // ---- batch-driven fill (fused kernel) ----
     // Inside the scene's rows most envelope entries own one to four pixels (every edge pixel of a line that runs along the
     // row is a site of its own), so walking the pixels and looking the owners up pays the bookkeeping per 32 pixels many
-    // times per batch of entries.  Here every lane takes one entry of a batch of 32 and writes the entry's first kHead
-    // pixels itself; the entries that own more are then taken one at a time by the whole warp (lane = pixel).
+    // times per batch of entries, and one plane with a thousand entries holds its warp (and the CTA's barrier) back.
     // The fused kernel first runs a resolve pass (warp = plane, batches in order, previous batch in registers): it turns
     // every entry into {base, v | first pixel << 16} and writes it back in place.  After that a batch is a self-contained
     // unit of work, and the batches of all planes are dealt to the warps: a plane with a thousand entries in this row no
@@ -677,37 +676,36 @@ struct RowFill {
         bend = bend_;
         be = load_raw(e0 + lane);
     }
-    static constexpr int kHead = 4;
     // writes the pixels of the batch inside [q0, q1) into trow (the tile row of this plane, pixel q0 at trow[0]) as float
-    // bits of the (exact) squared distances
+    // bits of the (exact) squared distances.  The batch owns the pixels [first pixel of its entry 0, bend); they are
+    // taken 32 at a time, lane = pixel: the owner of pixel p is the last entry that starts at or before p = (entries
+    // starting at or before the piece's first pixel) + (entries starting inside the piece up to p) - 1.  Pieces are
+    // independent of each other (no carry, no look-ahead), four are in flight per round.
     __device__ __forceinline__ void write_unit(int q0, int q1, uint32_t* __restrict__ trow, int lane) const {
-        const int s = (int)(be.y >> 16);                          // (sentinel lanes past the last entry: 0xFFFF, own nothing)
-        int send = __shfl_down_sync(0xffffffffu, s, 1);           // the next entry's first pixel ends this entry's interval
-        if (lane == 31) send = bend;
-        const int a = max(s, q0), b = min(send, q1);
-        const int len = b - a;
+        const int s = (int)(be.y >> 16);                          // (sentinel lanes past the last entry: 0xFFFF, never counted)
         const int v = (int)(be.y & 0xFFFFu);
         const uint32_t base = be.x;
-        uint32_t* tp = trow + (a - q0);
-#pragma unroll
-        for (int t = 0; t < kHead; ++t) {
-            if (t < len) {
-                const int dq = a + t - v;
-                tp[t] = __float_as_uint((float)(base + (uint32_t)(dq * dq)));
-            }
+        const int p_end = min(bend, q1);
+        const uint32_t le_mask = 0xFFFFFFFFu >> (31 - lane);
+        auto piece = [&](int p0) {
+            const int rel = s - p0;
+            const int nb = __popc(__ballot_sync(0xffffffffu, rel <= 0));
+            const unsigned marks = __reduce_or_sync(0xffffffffu, (unsigned)(rel - 1) < 31u ? 1u << rel : 0u);
+            const int idx = nb - 1 + __popc(marks & le_mask);
+            const int ov = __shfl_sync(0xffffffffu, v, idx);
+            const uint32_t ob = __shfl_sync(0xffffffffu, base, idx);
+            const int p = p0 + lane;
+            const int dq = p - ov;
+            if (p < p_end) trow[p - q0] = __float_as_uint((float)(ob + (uint32_t)(dq * dq)));
+        };
+        int p0 = max(__shfl_sync(0xffffffffu, s, 0), q0);
+        for (; p0 + 96 < p_end; p0 += 128) {
+            piece(p0);
+            piece(p0 + 32);
+            piece(p0 + 64);
+            piece(p0 + 96);
         }
-        unsigned lng = __ballot_sync(0xffffffffu, len > kHead);
-        while (lng) {
-            const int e = __ffs(lng) - 1;
-            lng &= lng - 1u;
-            const int ae = __shfl_sync(0xffffffffu, a, e) + kHead, bb = __shfl_sync(0xffffffffu, b, e);
-            const int ve = __shfl_sync(0xffffffffu, v, e);
-            const uint32_t base_e = __shfl_sync(0xffffffffu, base, e);
-            uint32_t* tq = trow + (ae + lane - q0);
-            int dq = ae + lane - ve;
-#pragma unroll 1                                                  // (typically one or two rounds: an unrolled body with its remainder code costs more)
-            for (int n = bb - ae - lane; n > 0; n -= 32, dq += 32, tq += 32) *tq = __float_as_uint((float)(base_e + (uint32_t)(dq * dq)));
-        }
+        for (; p0 < p_end; p0 += 32) piece(p0);
     }
 };
 
@@ -864,7 +862,11 @@ dt_fill_propagate_kernel(uint2* spill_all /* rewritten in place by the resolve p
             if (lane == 0) s_meta[d] = make_int4(meta.k_left, K, maxdepth - K, meta.right_start);
             const int nb = (K + 31) >> 5;
             for (int j = nb + lane; j <= kFPMaxBatches; j += 32) s_first[d][j] = 0xFFFF;
+#ifdef FDCM_AB_SKIP_RESOLVE
+            if (dm.W < 0) {
+#else
             if (K > 0) {
+#endif
                 RowFill rf;
                 rf.init(spill_all + prow * maxdepth, meta, maxdepth, lane);
                 uint2 nbe2 = rf.load_raw(64 + lane), nbe3 = rf.load_raw(96 + lane);

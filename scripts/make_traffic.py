@@ -6,8 +6,10 @@ import json
 import subprocess
 import sys
 
-NAMES = {"search_warp_kernel": "search", "dt_row_band_kernel": "dt_row_envelope", "dt_fill_propagate_kernel": "dt_fill_propagate",
-         "integral_tma_kernel": "integral", "dt_col_band_kernel": "dt_col_band", "dt_l1_propagate_kernel": "dt_l1_propagate",
+# (one build launches the envelope kernel twice -- scene bands on the second stream first, then the far bands -- and the fused
+# fill twice -- far rows first, then the scene rows: the n-th launch of a report maps to the n-th name)
+NAMES = {"search_warp_kernel": "search", "dt_row_band_kernel": ["dt_row_envelope", "dt_row_envelope_far"],
+         "dt_fill_propagate_kernel": ["dt_fill_propagate_far", "dt_fill_propagate"], "integral_tma_kernel": "integral", "dt_col_band_kernel": "dt_col_band", "dt_l1_propagate_kernel": "dt_l1_propagate",
          "raster_kernel": "raster", "topk_level1_kernel": "topk", "search_key_kernel": "search_order"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "sector": 1.0}
 out, src = {}, []
@@ -19,6 +21,8 @@ for rep in sys.argv[2:]:
     for r in rows[2:]:
         kname = r[col["Kernel Name"]]
         key = next((v for k, v in NAMES.items() if k in kname), None)
+        if isinstance(key, list):
+            key = next((k for k in key if k not in out), None)
         if key is None or key in out:
             continue
         val = lambda c: float(r[col[c]].replace(",", "")) * UNIT.get(units[col[c]], 1.0)
