@@ -832,12 +832,41 @@ __device__ __forceinline__ void propagate_from_tile(const uint32_t* tile, int ch
     for (int d = 0; d < D; ++d) op[(size_t)d * dm.plane_elems] = v[d];
 }
 
+// Resolve pass of the fused fill: one warp per (plane, row) walks the row's envelope batch by batch (previous batch in
+// registers, three batches of loads in flight), turns every entry into {base, v | first pixel << 16} -- right-stack entries
+// get their first pixel, chained bases are resolved -- and writes it back in place.  After this kernel every batch of 32
+// entries is a self-contained unit of work for dt_fill_propagate_kernel.  Rows [ya0, ya0 + na) then [yb0, ...).
+constexpr int kResolveWarps = 8;
+__global__ void __launch_bounds__(kResolveWarps * 32)
+dt_resolve_kernel(uint2* spill_all /* rewritten in place: no __restrict__, coherent loads */, const RowMeta* __restrict__ row_meta,
+                  MapDims dm, int maxdepth, int ya0, int na, int yb0, int n_rows) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * kResolveWarps + warp;             // plane-fastest: neighbouring warps, different planes of one row
+    if (w >= n_rows * dm.D) return;
+    const int ri = w / dm.D, d = w - ri * dm.D;
+    const int y = ri < na ? ya0 + ri : yb0 + (ri - na);
+    const int Hp = ((dm.H + 31) >> 5) << 5;
+    const size_t prow = (size_t)d * Hp + y;
+    const RowMeta meta = row_meta[prow];
+    const int K = meta.k_left + meta.k_right;
+    if (K <= 0) return;
+    RowFill rf;
+    rf.init(spill_all + prow * maxdepth, meta, maxdepth, lane);
+    uint2 nbe2 = rf.load_raw(64 + lane), nbe3 = rf.load_raw(96 + lane);
+    for (;;) {
+        rf.write_back(lane);
+        if (rf.e0 + 32 >= K) break;
+        __syncwarp();                                            // (later batches may look entries of this one up: slow_base_resolved)
+        rf.advance_resolved(lane, nbe2, nbe3);
+    }
+}
+
 constexpr int kFPMaxBatches = 96;        // envelope entries per row <= window width <= 2897 -> at most 91 batches of 32
 constexpr int kFPMaxChunks = 8;
 
 template <int D>
 __global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
-dt_fill_propagate_kernel(uint2* spill_all /* rewritten in place by the resolve pass: no __restrict__, coherent loads */,
+dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries (dt_resolve_kernel) */,
                          const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
                          MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first, int ya0, int na, int yb0) {
     using C = FPConfig<D>;
@@ -851,32 +880,20 @@ dt_fill_propagate_kernel(uint2* spill_all /* rewritten in place by the resolve p
     const int Hp = ((dm.H + 31) >> 5) << 5;                  // workspace rows per plane
     const int nchunks = (dm.W + C::kChunk - 1) / C::kChunk;
 
-    // ---- resolve pass (warp w: planes w and w + kWarps): resolved entries back in place, first pixel of every batch ----
+    // ---- first pixel of every batch (warp w: planes w and w + kWarps; the arrays hold resolved entries: dt_resolve_kernel) ----
 #pragma unroll
     for (int p = 0; p < C::kPlanesPerWarp; ++p) {
         const int d = warp + p * C::kWarps;
         if (d < D) {
             const size_t prow = (size_t)d * Hp + y;
             const RowMeta meta = row_meta[prow];
-            const int K = meta.k_left + meta.k_right;
-            if (lane == 0) s_meta[d] = make_int4(meta.k_left, K, maxdepth - K, meta.right_start);
+            const int K = meta.k_left + meta.k_right, roff = maxdepth - K;
+            if (lane == 0) s_meta[d] = make_int4(meta.k_left, K, roff, meta.right_start);
+            const uint2* row = spill_all + prow * maxdepth;
             const int nb = (K + 31) >> 5;
-            for (int j = nb + lane; j <= kFPMaxBatches; j += 32) s_first[d][j] = 0xFFFF;
-#ifdef FDCM_AB_SKIP_RESOLVE
-            if (dm.W < 0) {
-#else
-            if (K > 0) {
-#endif
-                RowFill rf;
-                rf.init(spill_all + prow * maxdepth, meta, maxdepth, lane);
-                uint2 nbe2 = rf.load_raw(64 + lane), nbe3 = rf.load_raw(96 + lane);
-                for (;;) {
-                    rf.write_back(lane);
-                    __syncwarp();                                // (later batches may look entries of this one up: slow_base_resolved)
-                    if (lane == 0) s_first[d][rf.e0 >> 5] = (uint16_t)(rf.be.y >> 16);
-                    if (rf.e0 + 32 >= K) break;
-                    rf.advance_resolved(lane, nbe2, nbe3);
-                }
+            for (int j = lane; j <= kFPMaxBatches; j += 32) {
+                const int i = 32 * j;
+                s_first[d][j] = (uint16_t)(j < nb ? row[i < meta.k_left ? i : i + roff].y >> 16 : 0xFFFFu);
             }
         }
     }
@@ -1152,6 +1169,16 @@ void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_
 }
 
 bool dt_fill_propagate_supported(const MapDims& dm) { return dm.D == 30; }
+
+// rows [ya0, ya1) and [yb0, yb1) of the image (pass 0, H, 0, 0 for every row); must precede launch_dt_fill_propagate
+void launch_dt_resolve(const MapDims& dm, void* d_ws, int win_lo, int win_hi, int ya0, int ya1, int yb0, int yb1, cudaStream_t s) {
+    const RowWs ws = row_ws(dm, d_ws, win_lo, win_hi);
+    const int na = max(0, ya1 - ya0), nb = max(0, yb1 - yb0);
+    if (na + nb <= 0) return;
+    const long long warps = (long long)(na + nb) * dm.D;
+    dt_resolve_kernel<<<(unsigned)((warps + kResolveWarps - 1) / kResolveWarps), kResolveWarps * 32, 0, s>>>(ws.spill, ws.row_k, dm, ws.maxdepth,
+                                                                                                        ya0, na, yb0, na + nb);
+}
 
 // rows [ya0, ya1) and [yb0, yb1) of the image (pass 0, H, 0, 0 for every row)
 void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,

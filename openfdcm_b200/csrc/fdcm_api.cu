@@ -605,10 +605,18 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
                 KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), sa);
                 launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, 1, sa);
             }
+            {
+                KernelScope k("dt_resolve", 2.0 * (double)dt_band_info_bytes(dm), sa);
+                launch_dt_resolve(dm, m->band_spill.p, m->col_lo, m->col_hi, ys0, ys1, 0, 0, sa);
+            }
             CUDA_TRY(cudaEventRecord(m->ev_join, sa));
             {
                 KernelScope k("dt_row_envelope_far", (double)dt_band_info_bytes(dm), s);
                 launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, 2, s);
+            }
+            {
+                KernelScope k("dt_resolve_far", 2.0 * (double)dt_band_info_bytes(dm), s);
+                launch_dt_resolve(dm, m->band_spill.p, m->col_lo, m->col_hi, 0, ys0, ys1, dm.H, s);
             }
             {
                 KernelScope k("dt_fill_propagate_far", N * (double)(dm.H - (ys1 - ys0)) / dm.H, s);
@@ -627,6 +635,10 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
                 launch_dt_row_envelope(m->band_info.p, nullptr, dm, m->band_spill.p, m->col_lo, m->col_hi, m->row_lo, m->row_hi, 0, s);
             }
             if (fused_propagate) {
+                {
+                    KernelScope k("dt_resolve", 2.0 * (double)dt_band_info_bytes(dm), s);
+                    launch_dt_resolve(dm, m->band_spill.p, m->col_lo, m->col_hi, 0, dm.H, 0, 0, s);
+                }
                 KernelScope k("dt_fill_propagate", N, s);
                 launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, 0, dm.H, 0, 0,
                                          s);

@@ -345,15 +345,45 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
                     const int off_lo = Ra < Rb ? 0 : Ra - Rb, off_hi = Ra < Rb ? Rb - Ra : 0;   // off of the first / last step ...
                     const int full_lo = max(off_lo, off_hi), full_hi = kICW + min(off_lo, off_hi);   // ... off is monotone between them
                     const int sub = lane >> 3, l8 = lane & 7;
-                    for (int r = full_lo + warp * 4 + sub; r < full_hi; r += kIConsumerWarps * 4) {
-                        const float4 v = *reinterpret_cast<const float4*>(tile + r * kIXBoxW + 4 * l8);
-                        *reinterpret_cast<float4*>(P + (long long)(ybase + r) * dm.pitch + xb + 4 * l8) = v;
+                    // (all shared-memory reads of a group first, then its global stores: the stores of one row do not wait
+                    // behind the read of the next)
+                    {
+                        constexpr int kG = 4;                                    // float4 rows per lane and round (<= 8 in all)
+                        const int r0 = full_lo + warp * 4 + sub;
+                        float* g4 = P + (long long)(ybase + r0) * dm.pitch + xb + 4 * l8;
+#pragma unroll
+                        for (int h = 0; h < kICW / (kIConsumerWarps * 4 * kG); ++h) {
+                            float4 v[kG];
+#pragma unroll
+                            for (int i = 0; i < kG; ++i) {
+                                const int r = r0 + (h * kG + i) * kIConsumerWarps * 4;
+                                if (r < full_hi) v[i] = *reinterpret_cast<const float4*>(tile + r * kIXBoxW + 4 * l8);
+                            }
+#pragma unroll
+                            for (int i = 0; i < kG; ++i) {
+                                const int r = r0 + (h * kG + i) * kIConsumerWarps * 4;
+                                if (r < full_hi) *reinterpret_cast<float4*>(g4 + (h * kG + i) * kIConsumerWarps * 4 * dm.pitch) = v[i];
+                            }
+                        }
                     }
                     float* gcol = P + (long long)ybase * dm.pitch + x;
-                    for (int r = warp; r < full_lo; r += kIConsumerWarps)                      // ragged rows above ...
-                        if ((unsigned)(r - off_m) < (unsigned)kICW) gcol[r * dm.pitch] = tile[r * kIXBoxW + lane];
-                    for (int r = full_hi + warp; r < kIXBoxH; r += kIConsumerWarps)            // ... and below the full rows
-                        if ((unsigned)(r - off_m) < (unsigned)kICW) gcol[r * dm.pitch] = tile[r * kIXBoxW + lane];
+                    // ragged rows above (r < full_lo <= kIRB) and below (r >= full_hi >= kICW) the full rows: at most kIRB each
+#pragma unroll
+                    for (int part = 0; part < 2; ++part) {
+                        constexpr int kR = kIRB / kIConsumerWarps;               // 8 rows per warp and part
+                        const int rb = part == 0 ? warp : full_hi + warp, re = part == 0 ? full_lo : kIXBoxH;
+                        float w[kR];
+#pragma unroll
+                        for (int i = 0; i < kR; ++i) {
+                            const int r = rb + i * kIConsumerWarps;
+                            if (r < re && (unsigned)(r - off_m) < (unsigned)kICW) w[i] = tile[r * kIXBoxW + lane];
+                        }
+#pragma unroll
+                        for (int i = 0; i < kR; ++i) {
+                            const int r = rb + i * kIConsumerWarps;
+                            if (r < re && (unsigned)(r - off_m) < (unsigned)kICW) gcol[r * dm.pitch] = w[i];
+                        }
+                    }
                 } else {
                     float* gp = P + (long long)(ybase + warp) * dm.pitch + x;
                     const float* tp = tile + warp * kIXBoxW + lane + xoff;

@@ -46,7 +46,8 @@ void dt_band_scene_rows(const MapDims& dm, int row_lo, int row_hi, int* y0, int*
 void launch_dt_row_fill(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, cudaStream_t s);
 // fill fused with propagateOrientation (and the L2 sqrt): the distance-transform planes never reach HBM
 bool dt_fill_propagate_supported(const MapDims& dm);
-// image rows [ya0, ya1) and [yb0, yb1)
+// image rows [ya0, ya1) and [yb0, yb1); the resolve pass rewrites the envelope arrays in place and must precede the fused fill
+void launch_dt_resolve(const MapDims& dm, void* d_ws, int win_lo, int win_hi, int ya0, int ya1, int yb0, int yb1, cudaStream_t s);
 void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, int win_lo, int win_hi, const PropParams& pp,
                               bool sqrt_first, int ya0, int ya1, int yb0, int yb1, cudaStream_t s);
 
