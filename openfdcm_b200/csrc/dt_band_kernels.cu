@@ -427,6 +427,25 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
         }
         __syncthreads();                                    // the mask is complete; the staging area becomes the ring
         cand = s_cand;
+        // split column of THIS band: the 32-column word at which half of its candidate columns have passed, so that the
+        // two warps (left stack ascending, right stack descending) get equal shares and neither waits at the join
+        {
+            int tot = 0;
+            for (int w = lane; w < dm.wwords; w += 32) tot += __popc(s_cand[w]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            int run = 0, split_w = dm.wwords;               // first word with (candidates before it) * 2 >= total
+            for (int w0 = 0; w0 < dm.wwords && split_w == dm.wwords; w0 += 32) {
+                const int c = w0 + lane < dm.wwords ? __popc(s_cand[w0 + lane]) : 0;
+                int inc = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+                const unsigned hit = __ballot_sync(0xffffffffu, 2 * (run + inc - c) >= tot);
+                if (hit) split_w = w0 + __ffs(hit) - 1;
+                run += __shfl_sync(0xffffffffu, inc, 31);
+            }
+            xsplit = min(dm.pitch, split_w * 32);
+        }
     }
 
     RowStack st;
