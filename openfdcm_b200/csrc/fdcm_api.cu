@@ -1076,8 +1076,14 @@ void fdcm_dt3::destroy_host_tset() {
     host_tset = nullptr;
 }
 
+// need_ranks: how many leading entries of every template's length order the caller will read (DefaultSearch only aligns the
+// max_tmpl_lines longest lines, defaultsearch.cpp:35-38); <= 0: the whole order.  When the need_ranks + 1 largest lengths
+// of a template are pairwise distinct, the leading ranks of ANY correct descending sort are the same as std::sort's, and a
+// selection scan yields them at a tenth of the cost; ties (or NaN) take the reference's std::sort, whose result for equal
+// keys depends on the algorithm.  (Host cores are shared by all ranks of a node: at 8 GPUs per 16 cores the full sort of
+// 5000 templates per step no longer hid behind the map build.)
 static void template_host_prep(const float* tl, const int32_t* off, int32_t T, std::vector<float>& line_len,
-                               std::vector<int32_t>& argsort, std::vector<float>& lengths) {
+                               std::vector<int32_t>& argsort, std::vector<float>& lengths, int need_ranks = 0) {
     const int64_t n = off[T];
     line_len.resize((size_t)n);
     argsort.resize((size_t)n);
@@ -1091,9 +1097,42 @@ static void template_host_prep(const float* tl, const int32_t* off, int32_t T, s
                 len[i] = line_length(tl + 4 * ((size_t)l0 + i));
                 idx[i] = i;
             }
+            lengths[(size_t)t] = eigen_sum(len, L);   // math.h:319-324
+            constexpr int kMaxSel = 8;
+            if (need_ranks > 0 && need_ranks < kMaxSel && need_ranks + 1 < L) {
+                // the need_ranks + 1 largest lengths, descending, by insertion into a short list
+                const int k = need_ranks + 1;
+                float top[kMaxSel];
+                int32_t at[kMaxSel];
+                int n = 0;
+                bool bad = false;                  // NaN among the lengths: no order to speak of
+                for (int i = 0; i < L; ++i) {
+                    const float v = len[i];
+                    if (v != v) { bad = true; break; }
+                    if (n == k && !(v > top[k - 1])) continue;    // (ties at or below the extra, k-th value do not touch the leading ranks)
+                    int j = n < k ? n : k - 1;
+                    while (j > 0 && v > top[j - 1]) { top[j] = top[j - 1]; at[j] = at[j - 1]; --j; }
+                    top[j] = v;
+                    at[j] = i;
+                    if (n < k) ++n;
+                }
+                bool distinct = !bad && n == k;
+                for (int j = 0; distinct && j + 1 < k; ++j) distinct = top[j] > top[j + 1];
+                if (distinct) {
+                    // ranks [0, need_ranks) as std::sort would give them; the remaining slots hold the other indices in
+                    // natural order (never read by a search with this max_tmpl_lines)
+                    int w = 0;
+                    for (int j = 0; j < need_ranks; ++j) idx[w++] = at[j];
+                    for (int i = 0; i < L; ++i) {
+                        bool used = false;
+                        for (int j = 0; j < need_ranks; ++j) used |= at[j] == i;
+                        if (!used) idx[w++] = i;
+                    }
+                    continue;
+                }
+            }
             // argsort(tmpl_lengths, std::greater<>()) (defaultsearch.cpp:35, math.h:107-116): same std::sort, same comparator
             std::sort(idx, idx + L, [len](int32_t const i1, int32_t const i2) { return len[i1] > len[i2]; });
-            lengths[(size_t)t] = eigen_sum(len, L);   // math.h:319-324
         }
     };
     if (T < 256) { work(0, T); return; }
@@ -1114,7 +1153,7 @@ static fdcm_status templates_ready(fdcm_templates* t, cudaStream_t s) {
 // Every consumer of a template set is host-synchronous (fdcm_search ends with a stream synchronisation), so no kernel can
 // still be reading the device arrays when they are overwritten here.
 static fdcm_status templates_load(fdcm_templates* t, const float* tmpl_lines, const int32_t* tmpl_offsets, int32_t n_tmpl,
-                                  cudaStream_t main_stream) {
+                                  cudaStream_t main_stream, int need_ranks = 0) {
     (void)main_stream;
     cudaStream_t s;
     if (fdcm_status st = get_copy_stream(t->device, &s)) return st;
@@ -1130,7 +1169,7 @@ static fdcm_status templates_load(fdcm_templates* t, const float* tmpl_lines, co
     t->denom_kind = -1;
     t->offsets.assign(tmpl_offsets, tmpl_offsets + n_tmpl + 1);
     for (int i = 0; i < n_tmpl; ++i) t->max_lines = std::max(t->max_lines, tmpl_offsets[i + 1] - tmpl_offsets[i]);
-    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, t->h_line_len, t->h_argsort, t->lengths);
+    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, t->h_line_len, t->h_argsort, t->lengths, need_ranks);
     cudaError_t e = t->lines.reserve(std::max<size_t>(16, (size_t)n * 16));
     if (e == cudaSuccess) e = t->offs.reserve((size_t)(n_tmpl + 1) * 4);
     if (e == cudaSuccess) e = t->argsort.reserve(std::max<size_t>(4, (size_t)n * 4));
@@ -1785,7 +1824,8 @@ static fdcm_status search_host_impl(const fdcm_dt3* m, const float* tmpl_lines, 
         m->host_tset->device = m->device;
     }
     static const int32_t zero_off[1] = {0};
-    if (fdcm_status st = templates_load(m->host_tset, tmpl_lines, n_tmpl ? tmpl_offsets : zero_off, n_tmpl, s)) return st;
+    // (this template set lives for this one search: only the ranks DefaultSearch / ConcentricRange will read are ordered)
+    if (fdcm_status st = templates_load(m->host_tset, tmpl_lines, n_tmpl ? tmpl_offsets : zero_off, n_tmpl, s, p ? p->max_tmpl_lines : 0)) return st;
     return search_impl(m, m->host_tset, scene, n_scene, p, out, capacity, n_out, comm);
 }
 

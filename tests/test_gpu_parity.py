@@ -169,6 +169,41 @@ def test_search_full_list_config1(batch):
     assert np.array_equal(got["score"], want["score"]), "scores within 1e-4 but not bit-exact"
 
 
+@pytest.mark.parametrize("max_t", [1, 2, 3, 4, 6, 9])
+def test_host_template_order_with_tied_lengths(max_t):
+    """fdcm_search_host only orders the max_tmpl_lines longest lines of a template (selection scan) and falls back to the
+    reference's std::sort when the leading lengths tie: templates full of equal-length lines (rectangles, repeated
+    segments, integer coordinates) must give the oracle's hypothesis list and matches for every max_tmpl_lines."""
+    rng = np.random.default_rng(77)
+    scene = synth_scene(640, 480, 200, seed=5)
+    tmpls = []
+    for k in range(40):
+        w, h = int(rng.integers(10, 60)), int(rng.integers(10, 60))
+        rect = np.array([[0, 0, w, 0], [w, 0, w, h], [w, h, 0, h], [0, h, 0, 0]], F32).T            # two pairs of equal lengths
+        extra = rng.integers(-40, 40, (4, int(rng.integers(0, 12)))).astype(F32)                    # integer end points: more ties
+        dup = rect[:, : int(rng.integers(0, 3))] + np.array([[3], [7], [3], [7]], F32)              # shifted copies: exact duplicates of lengths
+        t = np.concatenate([rect, extra, dup], axis=1)
+        tmpls.append(np.ascontiguousarray(t[:, rng.permutation(t.shape[1])], F32))
+    tmpls += synth_templates(10, 20, 640, seed=9)                                                   # and ordinary ones (selection path)
+    g = fdcm.build_cuda_featuremap(scene, fdcm.Dt3CudaParameters(30, 5.0, 1.5))
+    c = orc.Dt3Cpu(scene, 30, 5.0, 1.5)
+    import ctypes as C
+    from openfdcm_b200 import _lib
+    flat, off = fdcm._pack(tmpls)
+    sc = fdcm._records(scene)
+    p = _lib.SearchParams(max_t, 3, 10, 0, 0.0, 0, 0, 0, 0.0, 0.0, 0.0, 0.0)
+    out = np.zeros(2 * len(tmpls) * max_t * 3, fdcm.MATCH_DTYPE)
+    n = C.c_int64(0)
+    fdcm.check(_lib.lib().fdcm_search_host(g._h, fdcm.ptr(flat), fdcm.ptr(off), len(tmpls), fdcm.ptr(sc), sc.shape[0], C.byref(p),
+                                           fdcm.ptr(out), out.shape[0], C.byref(n)))
+    got = out[: n.value]
+    want, hyp = c.search(tmpls, scene, max_t, 3, batch=10, want_hyp=True)
+    assert np.array_equal(g.last_hypotheses(), hyp), "hypothesis set must be bit-exact"
+    assert np.array_equal(got["tmpl_idx"], want["tmpl_idx"])
+    assert np.array_equal(got["score"], want["score"], equal_nan=True)
+    assert np.array_equal(got["transform"], want["transform"], equal_nan=True)
+
+
 @pytest.mark.parametrize("dist", ["L2", "L2_SQUARED", "L1"])
 def test_search_top10(dist):
     scene, tmpls = _workload(77, n_tmpl=40, n_lines=25)
