@@ -946,9 +946,6 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
         {
             const int pref = s_pref[ch][lane], jl = s_jl[ch][lane];     // lane = plane
             const int n_units = __shfl_sync(0xffffffffu, pref, D);
-#ifdef FDCM_AB_SKIP_FILL
-            if (dm.W < 0)
-#endif
             {
                 // (the entries of the next unit are loaded before the current one is written: the L2 round trip of a unit
                 // hides behind the pixel stores of its predecessor)
@@ -985,9 +982,6 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
         }
         __syncthreads();
         // ---- propagate: one pixel per thread ----
-#ifdef FDCM_AB_SKIP_PROP
-        if (dm.W < 0)
-#endif
         propagate_from_tile<D>(fp_tile, C::kChunk, q0, y, planes, dm, pp, sqrt_first);
         __syncthreads();
     }

@@ -232,7 +232,7 @@ struct fdcm_dt3 {
     SlopeTableDev table_dev{};
     PropParams prop{};
     IntegralParams integ{};
-    DevBuf planes, mask, stack, lines, bins, rtab, band_info, band_spill, integ_items;
+    DevBuf planes, mask, stack, lines, bins, band_info, band_spill, integ_items;
     // lineIntegral plan (shift table, work items, tensor maps): a function of the map geometry and the planes pointer
     IntegralPlanDev integ_plan{};
     int plan_W = -1, plan_H = -1, plan_D = -1, plan_pitch = -1;
@@ -264,7 +264,7 @@ struct fdcm_dt3 {
 
     ~fdcm_dt3() {
         cudaSetDevice(device);
-        for (DevBuf* b : {&planes, &mask, &stack, &lines, &bins, &rtab, &band_info, &band_spill, &integ_items, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
+        for (DevBuf* b : {&planes, &mask, &stack, &lines, &bins, &band_info, &band_spill, &integ_items, &s_scene, &s_sorted_len, &s_sorted_idx, &s_hyp_off, &s_rec,
                           &s_valid, &s_hyp, &s_counters, &s_topk_score, &s_topk_idx, &s_topk_out, &s_topk_n, &s_keys, &s_keys2, &s_idx,
                           &s_perm, &s_sort_tmp})
             b->release();
@@ -401,9 +401,6 @@ static fdcm_status build_integral_plan(fdcm_dt3* m, cudaStream_t s) {
         int32_t* R = rtab.data() + (size_t)d * rlen;
         for (int i = 0; i < rlen; ++i) R[i] = (int32_t)(long long)std::round((float)i * r);
         if (mode != 1 && mode != 2) continue;
-#ifdef FDCM_AB_ONLY_MODE
-        if (mode != FDCM_AB_ONLY_MODE) continue;
-#endif
         const int n_major = mode == 1 ? dm.W : dm.H, n_minor = mode == 1 ? dm.H : dm.W;
         const int Rend = R[n_major - 1];
         const int cmin = Rend > 0 ? -Rend : 0, cmax = (Rend < 0 ? -Rend : 0) + n_minor - 1;
@@ -422,14 +419,10 @@ static fdcm_status build_integral_plan(fdcm_dt3* m, cudaStream_t s) {
     std::stable_sort(items.begin(), items.end(), [](const Item& a, const Item& b) { return a.work > b.work; });
     std::vector<int4> flat(items.size());
     for (size_t i = 0; i < items.size(); ++i) flat[i] = items[i].it;
-    CUDA_TRY(m->rtab.reserve(rtab.size() * sizeof(int32_t)));
     CUDA_TRY(m->integ_items.reserve(std::max<size_t>(16, flat.size() * sizeof(int4))));
-    CUDA_TRY(cudaMemcpyAsync(m->rtab.p, rtab.data(), rtab.size() * sizeof(int32_t), cudaMemcpyHostToDevice, s));
     if (!flat.empty()) CUDA_TRY(cudaMemcpyAsync(m->integ_items.p, flat.data(), flat.size() * sizeof(int4), cudaMemcpyHostToDevice, s));
     CUDA_TRY(cudaStreamSynchronize(s));   // the host vectors go out of scope (rare: only when the geometry changes)
     IntegralPlanDev& pl = m->integ_plan;
-    pl.rtab = m->rtab.as<int32_t>();
-    pl.rlen = rlen;
     pl.items4 = m->integ_items.as<int4>();
     pl.n_items = (int)flat.size();
     if (!integral_tma_encode(m->planes.p, dm, &pl.map_y, &pl.map_x))

@@ -30,13 +30,7 @@ constexpr int kIRB = 32;                        // major-axis steps per tile
 constexpr int kIYBoxW = kICW + kIRB + 4;        // y-major box: 164 columns x 32 rows (the box origin is rounded down to 16 bytes)
 constexpr int kIXBoxW = 36;                     // x-major box: 36 columns x 160 rows
 constexpr int kIXBoxH = kICW + kIRB;
-#ifndef FDCM_AB_ISTAGES
-#define FDCM_AB_ISTAGES 2
-#endif
-#ifndef FDCM_AB_IBLOCKS
-#define FDCM_AB_IBLOCKS 4
-#endif
-constexpr int kIStages = FDCM_AB_ISTAGES;
+constexpr int kIStages = 2;
 constexpr int kIStageFloats = kIXBoxW * kIXBoxH > kIYBoxW * kIRB ? kIXBoxW * kIXBoxH : kIYBoxW * kIRB;   // 5760 floats
 constexpr int kIConsumerWarps = kICW / 32;
 constexpr int kIThreads = kICW + 32;            // + the producer warp
@@ -48,10 +42,10 @@ __device__ __forceinline__ float lds_f32(uint32_t addr) {
     return v;
 }
 
-__global__ void __launch_bounds__(kIThreads, FDCM_AB_IBLOCKS)
+__global__ void __launch_bounds__(kIThreads, 4)
 integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_x,
                     float* __restrict__ planes, MapDims dm, const __grid_constant__ IntegralParams ip,
-                    const int32_t* __restrict__ rtab, int rlen, const int4* __restrict__ items, int n_items,
+                    const int4* __restrict__ items, int n_items,
                     int* __restrict__ counter) {
     extern __shared__ __align__(128) float stages[];          // [kIStages][kIStageFloats]
     __shared__ __align__(8) uint64_t bars[2 * kIStages];      // full[0..S), empty[S..2S)
@@ -113,12 +107,8 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
                     const uint32_t st = it % kIStages, ph = (it / kIStages) & 1u;
                     origin(b, cx, cy);                                        // (table loads done before the stage is free)
                     mbar_wait_backoff(empty0 + 8u * st, ph ^ 1u, 200);
-#ifdef FDCM_AB_SKIP_LOAD
-                    mbar_arrive(full0 + 8u * st);
-#else
                     mbar_arrive_expect_tx(full0 + 8u * st, bytes);
                     tma_load_3d(stage0 + st * (kIStageFloats * 4), map, cx, cy, d, full0 + 8u * st);
-#endif
                 }
             } else {
                 it += nblk;
@@ -149,9 +139,6 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
                 const bool inside = (unsigned)(c + Ra) < (unsigned)dm.W && (unsigned)(c + Rb) < (unsigned)dm.W;
                 const bool fast = __all_sync(0xffffffffu, inside && have);
                 mbar_wait_backoff(full0 + 8u * st, ph, 40);
-#ifdef FDCM_AB_SKIP_COMPUTE
-                if (dm.W > 0) { __syncwarp(); if (lane == 0) mbar_arrive(empty0 + 8u * st); continue; }
-#endif
                 // (addresses as opaque bases + small offsets: one address instruction per load and two per store; the loads
                 // of half a tile are issued together, then the dependent additions and the row stores)
                 uint32_t ta = smem_u32(tile);
@@ -229,14 +216,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
                 const bool interior = ncols == kIRB && ybase >= 0 && ybase + kIXBoxH <= dm.H;
                 const bool fast = __all_sync(0xffffffffu, have) && interior;
                 mbar_wait_backoff(full0 + 8u * st, ph, 40);
-#ifdef FDCM_AB_SKIP_COMPUTE
-                if (dm.W > 0) { __syncwarp(); if (lane == 0) mbar_arrive(empty0 + 8u * st); continue; }
-#endif
-#ifdef FDCM_AB_SKIP_XCOMP
-                if (dm.W < 0) {
-#else
                 if (fast) {
-#endif
                     // Interior tile.  The byte offset of step j relative to the chain's own tile row is the same for every
                     // chain: lane j puts it into the warp's table.  Slot s of the walk is step s - grp (the skew), so a lane
                     // reads the table through a pointer shifted by its lag.  The walk runs in chunks: all loads of a chunk,
@@ -276,11 +256,7 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
                             }
                         }
                     }
-#if defined(FDCM_AB_SKIP_XCOMP) || defined(FDCM_AB_XFAST_ONLY)
-                } else if (dm.W < 0) {
-#else
                 } else {
-#endif
                     // Tile at the image border (chains start / end inside it) or the last, narrower tile: the same chunked
                     // walk with per-lane predicates instead of branches.  A second table holds the tile row offset of every
                     // step: chain tid is inside the image at step j iff 0 <= ybase + tid + off_j < H.
@@ -331,9 +307,6 @@ integral_tma_kernel(const __grid_constant__ CUtensorMap map_y, const __grid_cons
                     }
                 }
                 named_bar_sync(1, kICW);                                       // every chain of the tile is summed
-#ifdef FDCM_AB_SKIP_XSTORE
-                if (dm.W > 0) { fence_proxy_async(); __syncwarp(); if (lane == 0) mbar_arrive(empty0 + 8u * st); continue; }
-#endif
                 // ---- store: tile row r, lane = memory column; the element belongs to chain (r - off of its step) ----
                 const int jl = fwd ? lane : kIRB - 1 - lane;                  // step of this lane's memory column
                 const int off_m = __shfl_sync(0xffffffffu, offl, jl);
@@ -416,7 +389,7 @@ void launch_integral_tma(float* d_planes, const MapDims& dm, const IntegralParam
     int per_sm = 2;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, integral_tma_kernel, kIThreads, smem) != cudaSuccess || per_sm < 1) per_sm = 2;
     const int grid = plan.n_items < per_sm * n_sms ? plan.n_items : per_sm * n_sms;
-    integral_tma_kernel<<<grid, kIThreads, smem, s>>>(plan.map_y, plan.map_x, d_planes, dm, ip, plan.rtab, plan.rlen, plan.items4,
+    integral_tma_kernel<<<grid, kIThreads, smem, s>>>(plan.map_y, plan.map_x, d_planes, dm, ip, plan.items4,
                                                       plan.n_items, plan.counter);
 }
 

@@ -18,8 +18,6 @@ void launch_propagate(float* d_planes, const MapDims& dm, const PropParams& pp, 
 
 // ---- integral_tma.cu: lineIntegral as one persistent TMA-fed kernel ----
 struct IntegralPlanDev {
-    const int32_t* rtab;         // [D][rlen] cumulative minor-axis shift R(i) = (long)roundf(i * r) per plane
-    int rlen;
     const int4* items4;          // (plane, first chain of the strip, first tile, end tile: where the strip meets the image), heaviest first
     int n_items;
     int* counter;                // work counter, zero before the launch
