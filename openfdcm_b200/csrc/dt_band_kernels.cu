@@ -391,12 +391,18 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
 
     const uint32_t* cand = nullptr;
     if (!kFromG) {
-        // ---- candidate phase: warp 0 takes the band's first row, warp 1 its last (existing) row ----
-        uint16_t* s_g = reinterpret_cast<uint16_t*>(band_smem) + (size_t)warp * dm.pitch;
-        const int rsel = warp == 0 ? 0 : min(31, dm.H - 1 - row0);
+        // ---- candidate phase ----
+        // A band inside the rows that can hold edge pixels needs both passes: warp 0 takes the band's first row, warp 1 its
+        // last (existing) row.  A band above all of them (b < band_lo) only needs its last row, a band below all of them its
+        // first row (every owner of its rows is an edge pixel on that one side): there the two warps share that single row,
+        // half of the columns each -- half the latency and half the instructions of the pass, and no survivors of a row
+        // that proves nothing.
+        const bool one_sided = b < band_lo || b > band_hi;     // (uniform over the CTA; the launcher widens [band_lo, band_hi] when unsure)
+        uint16_t* s_g = reinterpret_cast<uint16_t*>(band_smem) + (one_sided ? (size_t)0 : (size_t)warp * dm.pitch);
+        const int rsel = one_sided ? (b < band_lo ? min(31, dm.H - 1 - row0) : 0) : (warp == 0 ? 0 : min(31, dm.H - 1 - row0));
         const uint32_t mle = 0xFFFFFFFFu >> (31 - rsel), mge = 0xFFFFFFFFu << rsel;
         bool any = false;
-        for (int x0 = 0; x0 < dm.pitch; x0 += 32) {
+        for (int x0 = one_sided ? warp * 32 : 0; x0 < dm.pitch; x0 += one_sided ? 64 : 32) {
             const uint2 e = x0 + lane < dm.W ? info_row[x0] : make_uint2(0u, 0xFFFFFFFFu);
             uint32_t gv = 0xFFFFu;
             if (e.x != 0u || e.y != 0xFFFFFFFFu) {
@@ -408,17 +414,18 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
             }
             s_g[x0 + lane] = (uint16_t)gv;
             const uint32_t inside = __ballot_sync(0xffffffffu, e.x != 0u);
-            if (warp == 0 && lane == 0) s_cand[x0 >> 5] = inside;   // columns with an edge pixel inside the band
+            if ((one_sided || warp == 0) && lane == 0) s_cand[x0 >> 5] = inside;   // columns with an edge pixel inside the band
         }
         __syncthreads();
         // lane = column segment; the segment length in 16-bit words is 2 (mod 4): consecutive lanes hit different banks
-        int seg = (dm.W + 31) / 32;
+        const int nseg = one_sided ? 64 : 32;
+        int seg = (dm.W + nseg - 1) / nseg;
         seg += (2 - (seg & 3)) & 3;
         LooseRing lr;
         lr.init((uint32_t)__cvta_generic_to_shared(band_smem + (size_t)2 * dm.pitch * sizeof(uint16_t) +
                                                    (size_t)warp * kCandRing * 32 * sizeof(uint2)) + (uint32_t)lane * 8u);
-        if (__any_sync(0xffffffffu, any)) {
-            const int v0 = lane * seg, v1 = min(dm.W, v0 + seg);
+        if (one_sided || __any_sync(0xffffffffu, any)) {
+            const int v0 = (one_sided ? warp * 32 + lane : lane) * seg, v1 = min(dm.W, v0 + seg);
             for (int v = v0; v < v1; ++v) {
                 const int gv = s_g[v];
                 if (gv != 0xFFFF) lr.column(v, gv, Wm1, s_cand);

@@ -243,6 +243,54 @@ def band_candidates(mask, r0, band, seg, cap):
     return cand
 
 
+def band_candidates_one_sided(mask, r0, band, seg, cap, edges_below):
+    """A band with no edge pixel inside and all edge pixels on one side: only the loose pass over the row next to them
+    (the band's last row when they lie below it, its first row when they lie above), on 2x finer segments."""
+    h, w = mask.shape
+    r1 = min(r0 + band, h) - 1
+    g = _vertical_distance(mask, r1 if edges_below else r0)
+    cand = set()
+    for s0 in range(0, w, seg):
+        st = RingStack(cap)
+        for v in range(s0, min(s0 + seg, w)):
+            if g[v] != BIG:
+                st.column(v, int(g[v]), w - 1)
+        cand |= st.survivors()
+    return cand
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_one_sided_band_candidates_cover_every_row_of_the_band(seed):
+    """Bands above (below) every edge pixel of the plane: the survivors of ONE loose pass over the band's last (first) row
+    are a superset of the owners of each of its rows, and the envelope built from them alone fills every row exactly."""
+    rng = np.random.default_rng(900 + seed)
+    w, h = int(rng.integers(20, 100)), int(rng.integers(40, 90))
+    band, seg, cap = int(rng.choice([4, 8, 16])), int(rng.choice([3, 5, 9, 16])), int(rng.choice([1, 2, 4, 8]))
+    ylo, yhi = sorted(int(v) for v in rng.integers(h // 4, 3 * h // 4, 2))
+    mask = np.zeros((h, w), bool)
+    for _ in range(int(rng.integers(1, 9))):                          # edge pixels confined to rows [ylo, yhi]
+        x0, y0 = int(rng.integers(0, w)), int(rng.integers(ylo, yhi + 1))
+        dx, dy = int(rng.integers(-25, 26)), int(rng.integers(-8, 9))
+        for t in np.linspace(0, 1, 40):
+            x, y = int(round(x0 + t * dx)), int(round(y0 + t * dy))
+            if 0 <= x < w and ylo <= y <= yhi:
+                mask[y, x] = True
+    if seed % 3 == 0:
+        mask[ylo, :] = True                                           # a full horizontal line: every column is a vertex
+    if not mask.any():
+        mask[ylo, w // 2] = True
+    for r0 in range(0, h, band):
+        r1 = min(r0 + band, h) - 1
+        if r1 < ylo or r0 > yhi:                                      # one-sided band
+            cand = band_candidates_one_sided(mask, r0, band, seg, cap, edges_below=r1 < ylo)
+            for y in range(r0, r1 + 1):
+                g = _vertical_distance(mask, y)
+                assert _owners(g) <= cand, (seed, r0, y)
+                gp = np.where(np.isin(np.arange(w), list(cand)), g, BIG)
+                xs = int(rng.integers(0, w + 1))
+                assert np.array_equal(fill(joined_envelope(gp, xs), w), literal(g)), (seed, r0, y)
+
+
 @pytest.mark.parametrize("seed", range(10))
 def test_per_band_candidates_cover_every_row_of_the_band(seed):
     """An edge pixel above (below) a band that owns a pixel of one of its rows is strictly nearest on the open segment
