@@ -952,6 +952,26 @@ extern "C" fdcm_status fdcm_dt3_classify(const fdcm_dt3* m, const float* lines, 
 // =============================================================================================
 // template sets
 // =============================================================================================
+// grow-only page-locked host array: what the library uploads every search is written straight into pinned memory, so the
+// cudaMemcpyAsync of it neither stages through the driver nor holds the calling thread
+template <class T>
+struct PinnedVec {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t resize(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 64;
+        cudaError_t e = cudaMallocHost(reinterpret_cast<void**>(&p), want * sizeof(T));
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    T* data() { return p; }
+    ~PinnedVec() { if (p) cudaFreeHost(p); }
+};
+
 struct fdcm_templates {
     int device = 0;
     int32_t n_tmpl = 0;
@@ -959,8 +979,8 @@ struct fdcm_templates {
     int64_t n_lines = 0;
     std::vector<int32_t> offsets;     // host copy
     std::vector<float> lengths;       // getTemplateLengths
-    std::vector<float> h_line_len;    // host scratch kept for reloads
-    std::vector<int32_t> h_argsort;
+    PinnedVec<float> h_line_len;      // host scratch kept for reloads (pinned: uploaded every fdcm_search_host)
+    PinnedVec<int32_t> h_argsort;
     DevBuf lines, offs, argsort, line_len, denom;
     int denom_kind = -1;
     float denom_tau = 0.f;
@@ -1075,17 +1095,14 @@ void fdcm_dt3::destroy_host_tset() {
 // selection scan yields them at a tenth of the cost; ties (or NaN) take the reference's std::sort, whose result for equal
 // keys depends on the algorithm.  (Host cores are shared by all ranks of a node: at 8 GPUs per 16 cores the full sort of
 // 5000 templates per step no longer hid behind the map build.)
-static void template_host_prep(const float* tl, const int32_t* off, int32_t T, std::vector<float>& line_len,
-                               std::vector<int32_t>& argsort, std::vector<float>& lengths, int need_ranks = 0) {
-    const int64_t n = off[T];
-    line_len.resize((size_t)n);
-    argsort.resize((size_t)n);
+static void template_host_prep(const float* tl, const int32_t* off, int32_t T, float* line_len /* off[T] */,
+                               int32_t* argsort /* off[T] */, std::vector<float>& lengths, int need_ranks = 0) {
     lengths.resize((size_t)T);
     auto work = [&](int t0, int t1) {
         for (int t = t0; t < t1; ++t) {
             const int l0 = off[t], L = off[t + 1] - off[t];
-            float* len = line_len.data() + l0;
-            int32_t* idx = argsort.data() + l0;
+            float* len = line_len + l0;
+            int32_t* idx = argsort + l0;
             for (int i = 0; i < L; ++i) {
                 len[i] = line_length(tl + 4 * ((size_t)l0 + i));
                 idx[i] = i;
@@ -1162,7 +1179,9 @@ static fdcm_status templates_load(fdcm_templates* t, const float* tmpl_lines, co
     t->denom_kind = -1;
     t->offsets.assign(tmpl_offsets, tmpl_offsets + n_tmpl + 1);
     for (int i = 0; i < n_tmpl; ++i) t->max_lines = std::max(t->max_lines, tmpl_offsets[i + 1] - tmpl_offsets[i]);
-    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, t->h_line_len, t->h_argsort, t->lengths, need_ranks);
+    CUDA_TRY(t->h_line_len.resize((size_t)std::max<int64_t>(n, 1)));
+    CUDA_TRY(t->h_argsort.resize((size_t)std::max<int64_t>(n, 1)));
+    template_host_prep(tmpl_lines, tmpl_offsets, n_tmpl, t->h_line_len.data(), t->h_argsort.data(), t->lengths, need_ranks);
     cudaError_t e = t->lines.reserve(std::max<size_t>(16, (size_t)n * 16));
     if (e == cudaSuccess) e = t->offs.reserve((size_t)(n_tmpl + 1) * 4);
     if (e == cudaSuccess) e = t->argsort.reserve(std::max<size_t>(4, (size_t)n * 4));
