@@ -891,7 +891,7 @@ constexpr int kFPMaxBatches = 96;        // envelope entries per row <= window w
 constexpr int kFPMaxChunks = 8;
 
 template <int D>
-__global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
+__global__ void __launch_bounds__(FPConfig<D>::kThreads, 3)
 dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries (dt_resolve_kernel) */,
                          const RowMeta* __restrict__ row_meta, float* __restrict__ planes,
                          MapDims dm, int maxdepth, const __grid_constant__ PropParams pp, int sqrt_first, int ya0, int na, int yb0) {
@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__(kFillWarps * 32) dt_row_l1_band_kernel(const u
 
 // fused L1 row call + propagateOrientation: same structure as dt_fill_propagate_kernel
 template <int D>
-__global__ void __launch_bounds__(FPConfig<D>::kThreads, 2)
+__global__ void __launch_bounds__(FPConfig<D>::kThreads, 3)
 dt_l1_propagate_kernel(const uint2* __restrict__ info, float* __restrict__ planes, MapDims dm, int nbands,
                        const __grid_constant__ PropParams pp) {
     using C = FPConfig<D>;
