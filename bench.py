@@ -191,7 +191,10 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         comm = fd.Communicator.from_torch(local_rank)     # also bounds this rank's host pool to cores / world
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream shared by torch and the library: the CUDA events of timed() are recorded on the stream the
+    # kernels are launched on (torch's default stream has the null handle, which the library reads as "use your own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     fdcm.set_stream(local_rank, stream.cuda_stream)
     L = fdcm.lib()
 

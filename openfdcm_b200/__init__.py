@@ -85,7 +85,7 @@ class Dt3Cuda:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:   # (module globals are gone when the interpreter shuts down)
             lib().fdcm_dt3_release(h)
 
     def __copy__(self):
@@ -295,7 +295,7 @@ class TemplateSet:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:   # (module globals are gone when the interpreter shuts down)
             lib().fdcm_templates_release(h)
 
     def lengths(self):
@@ -356,7 +356,7 @@ class SceneBatch:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:   # (module globals are gone when the interpreter shuts down)
             lib().fdcm_scene_batch_destroy(h)
 
     def search_topk(self, scenes, templates, searcher, optimizer, penalty=None, k=10, tmpl_idx_base=0):

@@ -164,8 +164,29 @@ extern "C" fdcm_status fdcm_profile_reset(void) {
     g_prof_order.clear();
     return FDCM_OK;
 }
+// scopes of asynchronous calls (fdcm_dt3_rerun_async ...) that have finished by now: nobody synchronised inside the library
+static void prof_resolve_finished() {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    std::vector<ProfPending> keep;
+    for (auto& p : g_prof_pending) {
+        if (cudaEventQuery(p.b) != cudaSuccess) { keep.push_back(p); continue; }
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, p.a, p.b) == cudaSuccess) {
+            if (!g_prof.count(p.name)) g_prof_order.push_back(p.name);
+            auto& e = g_prof[p.name];
+            e.total_ms += ms;
+            e.launches += 1;
+            e.bytes = p.bytes;
+        }
+        cudaEventDestroy(p.a);
+        cudaEventDestroy(p.b);
+    }
+    g_prof_pending.swap(keep);
+}
+
 extern "C" fdcm_status fdcm_profile_count(int32_t* n) {
     if (!n) return fail(FDCM_ERR_INVALID, "n is null");
+    prof_resolve_finished();
     std::lock_guard<std::mutex> lk(g_mutex);
     *n = (int32_t)g_prof_order.size();
     return FDCM_OK;

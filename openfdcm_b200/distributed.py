@@ -44,7 +44,7 @@ class Communicator:
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and lib is not None:   # (module globals are gone when the interpreter shuts down)
             lib().fdcm_comm_destroy(h)
 
     def shard(self, n_items):
