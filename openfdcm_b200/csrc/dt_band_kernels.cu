@@ -997,74 +997,109 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
 // =============================================================================================
 // L1 transform (core/imgproc.h:137-146,178-184): the second (row) call is two min-plus sweeps, on integers
 // out(x) = min(x + min_{v<=x}(g(v) - v), -x + min_{v>=x}(g(v) + v)), g = vertical distance from the band records.
-// Lane = column.  A first right-to-left pass leaves the suffix minimum of g(v) + v per 32-column chunk in shared
-// memory; the fill then walks left to right with a warp prefix-min scan (carry across chunks) and a suffix-min
-// scan inside the chunk.  Exact at any map size; no envelope, no workspace.
+// A lane owns FOUR consecutive columns (two 16-byte loads of band records), a warp step covers 128 columns: the
+// prefix / suffix minima run serially over the lane's four values and only the lane totals go through the warp scan
+// (10 shuffles per 128 pixels instead of per 32).  A first right-to-left pass leaves the suffix minimum of g(v) + v per
+// 128-column chunk in shared memory; the fill then walks left to right with the prefix carried across chunks.
+// Exact at any map size; no envelope, no workspace.  (Columns in [W, pitch) hold "no edge" records: dt_col_band_kernel
+// writes every column of the pitch and the mask has no bit there.)
 // =============================================================================================
 constexpr int kBigL1 = 1 << 28;
+constexpr int kL1Cols = 128;                     // columns per warp step
 
 struct L1Fill {
-    const uint2* info;      // band records of (plane, band of the row), this lane's column of chunk 0: + lane
-    int* S;                 // shared: S[c] = min over columns >= 32c of g(v) + v, S[nchunks] = big
-    int r, W, pitch, carry;
+    const uint2* info;      // band records of (plane, band of the row), this lane's first column of chunk 0: + 4 * lane
+    int* S;                 // shared: S[c] = min over columns >= 128 c of g(v) + v, S[nchunks] = big
+    int r, pitch, carry;
     uint32_t mle, mge;
-    uint2 e_next;           // record of this lane's column in the next chunk to be visited (loaded one step ahead)
 
-    __device__ __forceinline__ uint2 load(int x) const {
-        return (x >= 0 && x < W) ? info[x - (int)(threadIdx.x & 31)] : make_uint2(0u, 0xFFFFFFFFu);
+    // records of the four columns x0 .. x0 + 3, x0 = q0 + 4 * lane (info already points at this lane's column of chunk 0)
+    __device__ __forceinline__ void load(int q0, int x0, uint4& a, uint4& b) const {
+        a = b = make_uint4(0u, 0xFFFFFFFFu, 0u, 0xFFFFFFFFu);
+        if (x0 < pitch) {                                      // (pitch is a multiple of 32: all four columns or none)
+            const uint4* p = reinterpret_cast<const uint4*>(info + q0);
+            a = p[0];
+            b = p[1];
+        }
     }
-    __device__ __forceinline__ int g_of(const uint2 e) const {   // vertical distance of this row in the record's column, or big
-        if (e.x == 0u && e.y == 0xFFFFFFFFu) return kBigL1;
-        const uint32_t above = e.x & mle, below = e.x & mge;
-        const int upd = r + (above ? __clz(above) - 31 : (int)(e.y & 0xFFFFu));
-        const int dnd = (31 - r) + (below ? __ffs(below) - 1 - 31 : (int)(e.y >> 16));
+    __device__ __forceinline__ int g_of(uint32_t ex, uint32_t ey) const {   // vertical distance of this row in the record's column, or big
+        if (ex == 0u && ey == 0xFFFFFFFFu) return kBigL1;
+        const uint32_t above = ex & mle, below = ex & mge;
+        const int upd = r + (above ? __clz(above) - 31 : (int)(ey & 0xFFFFu));
+        const int dnd = (31 - r) + (below ? __ffs(below) - 1 - 31 : (int)(ey >> 16));
         return min(upd, dnd);
     }
-    __device__ __forceinline__ void init(const uint2* info_row, int row_in_band, int width, int pitch_, int* s_suffix, int lane) {
-        info = info_row + lane;
+    __device__ __forceinline__ void bind(const uint2* info_row, int row_in_band, int pitch_, int* s_suffix) {
+        info = info_row;
         S = s_suffix;
         r = row_in_band;
-        W = width;
         pitch = pitch_;
         carry = kBigL1;
         mle = 0xFFFFFFFFu >> (31 - r);
         mge = 0xFFFFFFFFu << r;
-        const int nch = pitch >> 5;
+    }
+    // right-to-left pass: suffix minima of g(v) + v per chunk
+    __device__ __forceinline__ void init(int lane) {
+        const int nch = (pitch + kL1Cols - 1) / kL1Cols;
         int run = kBigL1;
         if (lane == 0) S[nch] = kBigL1;
-        uint2 e = load((nch - 1) * 32 + lane);
+        uint4 a, b;
+        load((nch - 1) * kL1Cols, (nch - 1) * kL1Cols + 4 * lane, a, b);
         for (int c = nch - 1; c >= 0; --c) {
-            const uint2 ec = e;
-            e = load((c - 1) * 32 + lane);
-            const int x = c * 32 + lane;
-            const int g = g_of(ec);
-            run = min(run, __reduce_min_sync(0xffffffffu, g >= kBigL1 ? kBigL1 : g + x));
+            const uint4 ca = a, cb = b;
+            if (c > 0) load((c - 1) * kL1Cols, (c - 1) * kL1Cols + 4 * lane, a, b);      // one chunk ahead
+            const int x0 = c * kL1Cols + 4 * lane;
+            const int g0 = g_of(ca.x, ca.y), g1 = g_of(ca.z, ca.w), g2 = g_of(cb.x, cb.y), g3 = g_of(cb.z, cb.w);
+            int m = g0 >= kBigL1 ? kBigL1 : g0 + x0;
+            m = min(m, g1 >= kBigL1 ? kBigL1 : g1 + x0 + 1);
+            m = min(m, g2 >= kBigL1 ? kBigL1 : g2 + x0 + 2);
+            m = min(m, g3 >= kBigL1 ? kBigL1 : g3 + x0 + 3);
+            run = min(run, __reduce_min_sync(0xffffffffu, m));
             if (lane == 0) S[c] = run;
         }
-        e_next = load(lane);
         __syncwarp();
     }
-    // value of pixel q0 + lane (0xFFFFFFFF: FLT_MAX); chunks must be visited left to right
-    __device__ __forceinline__ uint32_t chunk(int q0, int lane) {
-        const int x = q0 + lane;
-        const uint2 e = e_next;
-        e_next = load(x + 32);
-        const int g = g_of(e);
-        int a = g >= kBigL1 ? kBigL1 : g - x;
-        int b = g >= kBigL1 ? kBigL1 : g + x;
+    // values of the pixels q0 + 4 * lane .. + 3 (0xFFFFFFFF: FLT_MAX); chunks must be visited left to right
+    __device__ __forceinline__ void chunk(int q0, int lane, uint32_t out[4]) {
+        uint4 ea, eb;
+        load(q0, q0 + 4 * lane, ea, eb);
+        chunk(q0, lane, ea, eb, out);
+    }
+    // same with the records of the four columns already loaded
+    __device__ __forceinline__ void chunk(int q0, int lane, const uint4 ea, const uint4 eb, uint32_t out[4]) {
+        const int x0 = q0 + 4 * lane;
+        int g[4] = {g_of(ea.x, ea.y), g_of(ea.z, ea.w), g_of(eb.x, eb.y), g_of(eb.z, eb.w)};
+        int a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            a[i] = g[i] >= kBigL1 ? kBigL1 : g[i] - (x0 + i);
+            b[i] = g[i] >= kBigL1 ? kBigL1 : g[i] + (x0 + i);
+        }
+        a[1] = min(a[1], a[0]); a[2] = min(a[2], a[1]); a[3] = min(a[3], a[2]);     // prefix minima inside the lane
+        b[2] = min(b[2], b[3]); b[1] = min(b[1], b[2]); b[0] = min(b[0], b[1]);     // suffix minima inside the lane
+        int pa = a[3], pb = b[0];                                                    // lane totals -> inclusive warp scans
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const int ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_down_sync(0xffffffffu, b, o);
-            if (lane >= o) a = min(a, ta);
-            if (lane + o < 32) b = min(b, tb);
+            const int ta = __shfl_up_sync(0xffffffffu, pa, o), tb = __shfl_down_sync(0xffffffffu, pb, o);
+            if (lane >= o) pa = min(pa, ta);
+            if (lane + o < 32) pb = min(pb, tb);
         }
-        a = min(a, carry);
-        carry = __shfl_sync(0xffffffffu, a, 31);
-        b = min(b, S[(q0 >> 5) + 1]);
-        const int v = min(a + x, b - x);
-        return v >= (kBigL1 >> 1) ? 0xFFFFFFFFu : (uint32_t)v;
+        int xa = __shfl_up_sync(0xffffffffu, pa, 1), xb = __shfl_down_sync(0xffffffffu, pb, 1);   // exclusive: the lanes before / after
+        xa = min(lane == 0 ? kBigL1 : xa, carry);
+        xb = min(lane == 31 ? kBigL1 : xb, S[min(q0 / kL1Cols + 1, (pitch + kL1Cols - 1) / kL1Cols)]);   // (steps beyond the pitch: padding)
+        carry = min(carry, __shfl_sync(0xffffffffu, pa, 31));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int v = min(min(a[i], xa) + (x0 + i), min(b[i], xb) - (x0 + i));
+            out[i] = v >= (kBigL1 >> 1) ? 0xFFFFFFFFu : (uint32_t)v;
+        }
     }
 };
+
+__device__ __forceinline__ float4 l1_as_floats(const uint32_t u[4]) {
+    return make_float4(u[0] == 0xFFFFFFFFu ? FLT_MAX : (float)u[0], u[1] == 0xFFFFFFFFu ? FLT_MAX : (float)u[1],
+                       u[2] == 0xFFFFFFFFu ? FLT_MAX : (float)u[2], u[3] == 0xFFFFFFFFu ? FLT_MAX : (float)u[3]);
+}
 
 // stand-alone L1 row call: one warp per row
 __global__ void __launch_bounds__(kFillWarps * 32) dt_row_l1_band_kernel(const uint2* __restrict__ info, float* __restrict__ planes,
@@ -1074,43 +1109,76 @@ __global__ void __launch_bounds__(kFillWarps * 32) dt_row_l1_band_kernel(const u
     const int row = blockIdx.x * kFillWarps + warp;
     if (row >= n_rows_total) return;
     const int d = row / dm.H, y = row % dm.H;
-    const int nch = dm.pitch >> 5;
+    const int nch = (dm.pitch + kL1Cols - 1) / kL1Cols;
     L1Fill lf;
-    lf.init(info + ((size_t)d * nbands + (y >> 5)) * dm.pitch, y & 31, dm.W, dm.pitch, l1_suffix + warp * (nch + 1), lane);
-    float* op = planes + (size_t)row * dm.pitch + lane;
-    for (int q0 = 0; q0 < dm.pitch; q0 += 32, op += 32) {
-        const uint32_t v = lf.chunk(q0, lane);
-        if (q0 + lane < dm.W) *op = v == 0xFFFFFFFFu ? FLT_MAX : (float)v;
+    lf.bind(info + ((size_t)d * nbands + (y >> 5)) * dm.pitch + 4 * lane, y & 31, dm.pitch, l1_suffix + warp * (nch + 1));
+    lf.init(lane);
+    float* op = planes + (size_t)row * dm.pitch + 4 * lane;
+    for (int q0 = 0; q0 < dm.pitch; q0 += kL1Cols, op += kL1Cols) {
+        uint32_t u[4];
+        lf.chunk(q0, lane, u);
+        if (q0 + 4 * lane < dm.pitch) *reinterpret_cast<float4*>(op) = l1_as_floats(u);   // (columns in [W, pitch) are padding)
     }
 }
 
-// fused L1 row call + propagateOrientation: same structure as dt_fill_propagate_kernel
+// fused L1 row call + propagateOrientation: CTA per image row, 512-pixel chunks.  Fill: warp w < 15 takes planes w and
+// w + 15, four 128-column steps per plane and chunk, one 16-byte tile store per lane and step.  Propagate: one pixel per
+// thread (propagate_from_tile).
 template <int D>
-__global__ void __launch_bounds__(FPConfig<D>::kThreads, 3)
+struct L1Config {
+    static constexpr int kThreads = 512;
+    static constexpr int kChunk = kThreads;
+    static constexpr int kFillWarps = (D + 1) / 2;           // two planes per filling warp
+    static_assert(kFillWarps * 32 <= kThreads, "");
+};
+
+#ifndef FDCM_AB_L1_MINB
+#define FDCM_AB_L1_MINB 3
+#endif
+template <int D>
+__global__ void __launch_bounds__(L1Config<D>::kThreads, FDCM_AB_L1_MINB)
 dt_l1_propagate_kernel(const uint2* __restrict__ info, float* __restrict__ planes, MapDims dm, int nbands,
                        const __grid_constant__ PropParams pp) {
-    using C = FPConfig<D>;
+    using C = L1Config<D>;
     extern __shared__ __align__(16) uint32_t fp_tile[];      // [D][kChunk] distances, then [D][nchunks + 1] suffix minima
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = blockIdx.x;
-    const int nch = dm.pitch >> 5;
+    const int nch = (dm.pitch + kL1Cols - 1) / kL1Cols;
     int* suffix = reinterpret_cast<int*>(fp_tile + (size_t)D * C::kChunk);
-    L1Fill lf[C::kPlanesPerWarp];
+    // (per-plane state is the carried prefix minimum only; everything else is recomputed from d)
+    int carry[2] = {kBigL1, kBigL1};
+    const bool filler = warp < C::kFillWarps;
+    auto plane_fill = [&](int d) {
+        L1Fill lf;
+        lf.bind(info + ((size_t)d * nbands + (y >> 5)) * dm.pitch + 4 * lane, y & 31, dm.pitch, suffix + d * (nch + 1));
+        return lf;
+    };
 #pragma unroll
-    for (int p = 0; p < C::kPlanesPerWarp; ++p) {
-        const int d = warp + p * C::kWarps;
-        if (d < D) lf[p].init(info + ((size_t)d * nbands + (y >> 5)) * dm.pitch, y & 31, dm.W, dm.pitch, suffix + d * (nch + 1), lane);
+    for (int p = 0; p < 2; ++p) {
+        const int d = warp + p * C::kFillWarps;
+        if (filler && d < D) plane_fill(d).init(lane);
     }
     for (int q0 = 0; q0 < dm.W; q0 += C::kChunk) {
 #pragma unroll
-        for (int p = 0; p < C::kPlanesPerWarp; ++p) {
-            const int d = warp + p * C::kWarps;
-            if (d < D) {
-                uint32_t* trow = fp_tile + (size_t)d * C::kChunk + lane;
-                for (int c = 0; c < C::kChunk; c += 32) {
-                    const uint32_t u = (q0 + c < dm.pitch) ? lf[p].chunk(q0 + c, lane) : 0xFFFFFFFFu;
-                    trow[c] = __float_as_uint(u == 0xFFFFFFFFu ? FLT_MAX : (float)u);
+        for (int p = 0; p < 2; ++p) {
+            const int d = warp + p * C::kFillWarps;
+            if (filler && d < D) {
+                L1Fill lf = plane_fill(d);
+                lf.carry = carry[p];
+                float4* trow = reinterpret_cast<float4*>(fp_tile + (size_t)d * C::kChunk) + lane;
+                // (the records of the next step are loaded before the current one is computed; beyond the pitch load() yields
+                // "no edge" records and the step writes FLT_MAX into tile columns nobody reads)
+                uint4 ra, rb;
+                lf.load(q0, q0 + 4 * lane, ra, rb);
+#pragma unroll
+                for (int c = 0; c < C::kChunk; c += kL1Cols) {
+                    const uint4 ca = ra, cb = rb;
+                    if (c + kL1Cols < C::kChunk) lf.load(q0 + c + kL1Cols, q0 + c + kL1Cols + 4 * lane, ra, rb);
+                    uint32_t u[4];
+                    lf.chunk(q0 + c, lane, ca, cb, u);
+                    trow[c / 4] = l1_as_floats(u);
                 }
+                carry[p] = lf.carry;
             }
         }
         __syncthreads();
@@ -1215,14 +1283,14 @@ void launch_dt_fill_propagate(float* d_planes, const MapDims& dm, void* d_ws, in
 
 void launch_dt_row_l1_band(const void* d_info, float* d_planes, const MapDims& dm, cudaStream_t s) {
     const int nbands = dt_band_count(dm), rows = dm.D * dm.H;
-    const size_t smem = (size_t)kFillWarps * ((dm.pitch >> 5) + 1) * sizeof(int);
+    const size_t smem = (size_t)kFillWarps * ((dm.pitch + kL1Cols - 1) / kL1Cols + 1) * sizeof(int);
     dt_row_l1_band_kernel<<<cdiv_u(rows, kFillWarps), kFillWarps * 32, smem, s>>>(reinterpret_cast<const uint2*>(d_info), d_planes, dm,
                                                                                  nbands, rows);
 }
 
 void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& dm, const PropParams& pp, cudaStream_t s) {
-    using C = FPConfig<30>;
-    const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch >> 5) + 1) * sizeof(int);
+    using C = L1Config<30>;
+    const size_t smem = (size_t)30 * C::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch + kL1Cols - 1) / kL1Cols + 1) * sizeof(int);
     cudaFuncSetAttribute(dt_l1_propagate_kernel<30>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     dt_l1_propagate_kernel<30><<<dm.H, C::kThreads, smem, s>>>(reinterpret_cast<const uint2*>(d_info), d_planes, dm, dt_band_count(dm), pp);
 }
@@ -1231,7 +1299,7 @@ void launch_dt_l1_propagate(const void* d_info, float* d_planes, const MapDims& 
 // first-generation kernels when it exceeds what one CTA can have
 size_t dt_band_smem_bytes(const MapDims& dm) {
     const size_t col = (size_t)dt_band_count(dm) * 64 * 6;
-    const size_t l1 = (size_t)30 * FPConfig<30>::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch >> 5) + 1) * sizeof(int);
+    const size_t l1 = (size_t)30 * L1Config<30>::kChunk * sizeof(uint32_t) + (size_t)30 * ((dm.pitch + kL1Cols - 1) / kL1Cols + 1) * sizeof(int);
     const size_t env = band_alias_bytes(dm.pitch) + (size_t)dm.wwords * sizeof(uint32_t);
     return std::max(std::max(col, l1), env);
 }

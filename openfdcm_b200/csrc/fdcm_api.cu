@@ -95,8 +95,12 @@ static fdcm_status get_aux_stream(int device, cudaStream_t* s) {
     std::lock_guard<std::mutex> lk(g_mutex);
     auto o = g_aux_streams.find(device);
     if (o == g_aux_streams.end()) {
+        // highest priority: what runs here (the scene bands' envelopes and their resolve pass) is the long pole of a build,
+        // its CTAs must not queue behind the pending CTAs of the far rows' fill on the main stream
         cudaStream_t ns;
-        CUDA_TRY(cudaStreamCreateWithFlags(&ns, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&ns, cudaStreamNonBlocking, prio_hi));
         o = g_aux_streams.emplace(device, ns).first;
     }
     *s = o->second;
@@ -608,7 +612,8 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
         if (split) {
             // The envelopes of the bands that hold the scene's edge rows are the long pole of the build (serial column chains,
             // ~half of the issue slots idle); the rows of the other (far) bands only need the cheap far envelopes.  So the scene
-            // envelopes run on a second stream while the main stream fills + propagates the far rows under them.
+            // envelopes, their resolve pass and their fill run on a second stream while the main stream fills + propagates the
+            // far rows under them.
             cudaStream_t sa;
             if (fdcm_status st = get_aux_stream(m->device, &sa)) return st;
             if (!m->ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
@@ -622,6 +627,13 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
             {
                 KernelScope k("dt_resolve", 2.0 * (double)dt_band_info_bytes(dm), sa);
                 launch_dt_resolve(dm, m->band_spill.p, m->col_lo, m->col_hi, ys0, ys1, 0, 0, sa);
+            }
+            {
+                // (same stream: the scene rows' fill starts as soon as their envelopes are resolved and shares the GPU with the
+                // tail of the far rows' fill instead of waiting behind it)
+                KernelScope k("dt_fill_propagate", N * (double)(ys1 - ys0) / dm.H, sa);
+                launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, ys0, ys1, 0,
+                                         0, sa);
             }
             CUDA_TRY(cudaEventRecord(m->ev_join, sa));
             {
@@ -638,11 +650,6 @@ static fdcm_status run_build_kernels(fdcm_dt3* m, cudaStream_t s) {
                                          dm.H, s);
             }
             CUDA_TRY(cudaStreamWaitEvent(s, m->ev_join, 0));
-            {
-                KernelScope k("dt_fill_propagate", N * (double)(ys1 - ys0) / dm.H, s);
-                launch_dt_fill_propagate(m->planes.as<float>(), dm, m->band_spill.p, m->col_lo, m->col_hi, m->prop, dist == FDCM_L2, ys0, ys1, 0,
-                                         0, s);
-            }
         } else {
             {
                 KernelScope k("dt_row_envelope", (double)dt_band_info_bytes(dm), s);
