@@ -1559,8 +1559,8 @@ static fdcm_status search_impl(const fdcm_dt3* m, const fdcm_templates* tc, cons
     if (H >= 4096 && H < (int64_t)1 << 31) {
         // process the hypotheses in the spatial order of their scene lines (L2 locality of the map gathers)
         const float ex = m->s_scene_max[0] - m->s_scene_min[0], ey = m->s_scene_max[1] - m->s_scene_min[1];
-        const int cells_x = std::min(4096, std::max(1, (int)(ex / 128.f) + 1));
-        const int cells_y = std::min(4096, std::max(1, (int)(ey / 128.f) + 1));
+        const int cells_x = std::min(4096, std::max(1, (int)(ex / (float)kSearchCellW) + 1));
+        const int cells_y = std::min(4096, std::max(1, (int)(ey / (float)kSearchCellH) + 1));
         int key_bits = 1;
         while (((int64_t)1 << key_bits) < (int64_t)cells_x * cells_y) ++key_bits;
         const size_t tmp = search_order_temp_bytes(H);

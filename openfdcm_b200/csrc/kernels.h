@@ -99,6 +99,12 @@ struct SearchOutputs {
 };
 
 // spatial ordering of the hypotheses (locality of the map gathers): keys + radix sort -> permutation
+// Cell of the spatial hypothesis order (search_key_kernel).  The hypotheses are processed cell row by cell row, x fastest:
+// the map rows a cell row reaches (its own height + twice the template radius, all D planes) slide through the L2 once per
+// cell row, so tall cells re-read the map fewer times, as long as the window (rows reached x columns of the cells in
+// flight) still fits the L2.  Measured on config 3 (1080p, D = 30, templates reaching +-270 px): 128 x 128 -> 1.174 ms,
+// 128 x 256 -> 1.149, 128 x 384 -> 1.070, 128 x 512 -> 1.145, 128 x 720 -> 1.067, one row of 32-px columns -> 1.090.
+constexpr int kSearchCellW = 128, kSearchCellH = 384;
 size_t search_order_temp_bytes(int64_t n_hyp);
 void launch_search_order(const TemplatesView& tv, const SceneView& sv, const SearchLaunch& sl, uint32_t* d_keys, uint32_t* d_keys_out,
                          int32_t* d_idx, int32_t* d_perm, void* d_temp, size_t temp_bytes, float minx, float miny, int cells_x,

@@ -161,7 +161,7 @@ __device__ __forceinline__ HypDecode decode_hypothesis(long long h, const Templa
     return r;
 }
 
-// Spatial sort key of a hypothesis: the 128-pixel cell (row-major) of the centre of its scene line.  All
+// Spatial sort key of a hypothesis: the cell (kSearchCellW x kSearchCellH pixels, row-major) of the centre of its scene line.  All
 // hypotheses aligned on nearby scene lines gather from the same neighbourhood of the map, so processing them
 // together keeps that neighbourhood (all D planes) resident in L2.  The order only affects scheduling; results
 // are written at the hypothesis index.
@@ -173,8 +173,8 @@ __global__ void search_key_kernel(const __grid_constant__ TemplatesView tv, cons
     const HypDecode d = decode_hypothesis(h, tv, sv, sl);
     hyp[h] = make_int4(d.t + sl.tmpl_idx_base, d.tline, d.sline, d.rev);   // the search kernel reads it back
     const float4 s = sv.lines[d.sline];
-    const int cx = min(max((int)(((s.x + s.z) * 0.5f - minx) * (1.f / 128.f)), 0), cells_x - 1);
-    const int cy = min(max((int)(((s.y + s.w) * 0.5f - miny) * (1.f / 128.f)), 0), 4095);
+    const int cx = min(max((int)(((s.x + s.z) * 0.5f - minx) * (1.f / (float)kSearchCellW)), 0), cells_x - 1);
+    const int cy = min(max((int)(((s.y + s.w) * 0.5f - miny) * (1.f / (float)kSearchCellH)), 0), 4095);
     keys[h] = (uint32_t)(cy * cells_x + cx);
     idx[h] = (int32_t)h;
 }
