@@ -31,11 +31,27 @@ constexpr uint32_t kNone16 = 0xFFFFu;
 // per (plane, band, column): {edge bits of the 32 rows, (rows from the band's first row up to the last edge above) |
 // (rows from the band's last row down to the first edge below) << 16}; 0xFFFF = no such edge
 // =============================================================================================
+// 32 x 32 bit-matrix transposition across a warp: lane r holds row word a (bit c = column c); afterwards lane c holds the
+// column word (bit r = row r).  Five butterfly steps swap the off-diagonal blocks of size 16, 8, 4, 2, 1.
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t a, int lane) {
+    uint32_t m = 0x0000FFFFu;                                  // bits whose column index has bit j clear
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, a, j);
+        a = (lane & j) ? (a & ~m) | ((y >> j) & m) : (a & m) | ((y << j) & ~m);
+        m ^= m << (j >> 1);                                    // 0x0000FFFF -> 0x00FF00FF -> 0x0F0F0F0F -> 0x33333333 -> 0x55555555
+    }
+    return a;
+}
+
+constexpr int kColSegs = 4;                                    // band segments walked in parallel per column
+
 __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __restrict__ mask, MapDims dm,
                                                           uint2* __restrict__ info, int nbands) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint32_t* M = reinterpret_cast<uint32_t*>(smem_raw);                       // [nbands][64] column bit words
     uint16_t* up16 = reinterpret_cast<uint16_t*>(M + (size_t)nbands * 64);     // [nbands][64]
+    __shared__ int s_last[kColSegs][64], s_first[kColSegs][64];                // per segment and column: last / first edge row (-1: none)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     const int d = blockIdx.y;
     const int w0 = blockIdx.x * 2;                                             // first mask word (32 columns each)
@@ -50,38 +66,45 @@ __global__ void __launch_bounds__(256) dt_col_band_kernel(const uint32_t* __rest
         }
         uint32_t c0 = 0, c1 = 0;
         if (__any_sync(0xffffffffu, (a0 | a1) != 0)) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const uint32_t m0 = __ballot_sync(0xffffffffu, (a0 >> c) & 1u);
-                const uint32_t m1 = __ballot_sync(0xffffffffu, (a1 >> c) & 1u);
-                if (lane == c) { c0 = m0; c1 = m1; }
-            }
+            c0 = warp_bit_transpose(a0, lane);
+            c1 = warp_bit_transpose(a1, lane);
         }
         M[(size_t)b * 64 + lane] = c0;
         M[(size_t)b * 64 + 32 + lane] = c1;
     }
     __syncthreads();
-    // ---- nearest edge above / below every band, per column ----
-    if (threadIdx.x < 64) {
-        const int c = threadIdx.x;
-        const int x = blockIdx.x * 64 + c;
-        int last = -1, first = 0x7FFFFFF0;
-        for (int b = 0; b < nbands; ++b) {
-            up16[(size_t)b * 64 + c] = (uint16_t)(last < 0 ? kNone16 : (uint32_t)(b * 32 - last));
+    // ---- nearest edge above / below every band, per column: thread = (segment of bands, column) ----
+    const int c = threadIdx.x & 63, seg = threadIdx.x >> 6;
+    const int per = (nbands + kColSegs - 1) / kColSegs;
+    const int b0 = min(nbands, seg * per), b1 = min(nbands, b0 + per);
+    {
+        int last = -1, first = -1;
+        for (int b = b0; b < b1; ++b) {
             const uint32_t m = M[(size_t)b * 64 + c];
             if (m) {
-                if (last < 0) first = b * 32 + __ffs(m) - 1;
+                if (first < 0) first = b * 32 + __ffs(m) - 1;
                 last = b * 32 + 31 - __clz(m);
             }
         }
-        int next = -1;
-        uint2* out = info + (size_t)d * nbands * dm.pitch + x;
-        for (int b = nbands - 1; b >= 0; --b) {
-            const uint32_t m = M[(size_t)b * 64 + c];
-            const uint32_t dd = next < 0 ? kNone16 : (uint32_t)(next - (b * 32 + 31));
-            if (x < dm.pitch) out[(size_t)b * dm.pitch] = make_uint2(m, (uint32_t)up16[(size_t)b * 64 + c] | (dd << 16));
-            if (m) next = b * 32 + __ffs(m) - 1;
-        }
+        s_last[seg][c] = last;
+        s_first[seg][c] = first;
+    }
+    __syncthreads();
+    int last = -1, next = -1;                                                  // last edge row before / first edge row after the segment
+    for (int sg = 0; sg < seg; ++sg) { const int v = s_last[sg][c]; if (v >= 0) last = v; }
+    for (int sg = kColSegs - 1; sg > seg; --sg) { const int v = s_first[sg][c]; if (v >= 0) next = v; }
+    for (int b = b0; b < b1; ++b) {
+        up16[(size_t)b * 64 + c] = (uint16_t)(last < 0 ? kNone16 : (uint32_t)(b * 32 - last));
+        const uint32_t m = M[(size_t)b * 64 + c];
+        if (m) last = b * 32 + 31 - __clz(m);
+    }
+    const int x = blockIdx.x * 64 + c;
+    uint2* out = info + (size_t)d * nbands * dm.pitch + x;
+    for (int b = b1 - 1; b >= b0; --b) {
+        const uint32_t m = M[(size_t)b * 64 + c];
+        const uint32_t dd = next < 0 ? kNone16 : (uint32_t)(next - (b * 32 + 31));
+        if (x < dm.pitch) out[(size_t)b * dm.pitch] = make_uint2(m, (uint32_t)up16[(size_t)b * 64 + c] | (dd << 16));
+        if (m) next = b * 32 + __ffs(m) - 1;
     }
 }
 
