@@ -6,10 +6,10 @@ import json
 import subprocess
 import sys
 
-# (one build launches the envelope kernel twice -- scene bands on the second stream first, then the far bands -- and the fused
-# fill twice -- far rows first, then the scene rows: the n-th launch of a report maps to the n-th name)
+# (one build launches the envelope kernel, the resolve pass and the fused fill twice each -- scene bands / rows on the second
+# stream first, then the far ones: the n-th launch of a report maps to the n-th name)
 NAMES = {"search_warp_kernel": "search", "dt_row_band_kernel": ["dt_row_envelope", "dt_row_envelope_far"],
-         "dt_fill_propagate_kernel": ["dt_fill_propagate_far", "dt_fill_propagate"], "integral_tma_kernel": "integral",
+         "dt_fill_propagate_kernel": ["dt_fill_propagate", "dt_fill_propagate_far"], "integral_tma_kernel": "integral",
          "dt_resolve_kernel": ["dt_resolve", "dt_resolve_far"], "dt_col_band_kernel": "dt_col_band", "dt_l1_propagate_kernel": "dt_l1_propagate",
          "raster_kernel": "raster", "topk_level1_kernel": "topk", "search_key_kernel": "search_order"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "sector": 1.0}
