@@ -1140,7 +1140,15 @@ __global__ void __launch_bounds__(kFillWarps * 32) dt_row_l1_band_kernel(const u
     for (int q0 = 0; q0 < dm.pitch; q0 += kL1Cols, op += kL1Cols) {
         uint32_t u[4];
         lf.chunk(q0, lane, u);
-        if (q0 + 4 * lane < dm.pitch) *reinterpret_cast<float4*>(op) = l1_as_floats(u);   // (columns in [W, pitch) are padding)
+        const int x0 = q0 + 4 * lane;
+        const float4 f = l1_as_floats(u);
+        if (x0 + 3 < dm.W) {
+            *reinterpret_cast<float4*>(op) = f;
+        } else {                                             // the last columns of the row: nothing is written beyond W
+            if (x0 < dm.W) op[0] = f.x;
+            if (x0 + 1 < dm.W) op[1] = f.y;
+            if (x0 + 2 < dm.W) op[2] = f.z;
+        }
     }
 }
 
