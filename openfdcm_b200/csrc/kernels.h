@@ -102,8 +102,11 @@ struct SearchOutputs {
 // Cell of the spatial hypothesis order (search_key_kernel).  The hypotheses are processed cell row by cell row, x fastest:
 // the map rows a cell row reaches (its own height + twice the template radius, all D planes) slide through the L2 once per
 // cell row, so tall cells re-read the map fewer times, as long as the window (rows reached x columns of the cells in
-// flight) still fits the L2.  Measured on config 3 (1080p, D = 30, templates reaching +-270 px): 128 x 128 -> 1.174 ms,
-// 128 x 256 -> 1.149, 128 x 384 -> 1.070, 128 x 512 -> 1.145, 128 x 720 -> 1.067, one row of 32-px columns -> 1.090.
+// flight) still fits the L2.  Measured on config 3 (1080p, D = 30, templates reaching +-270 px), search kernel alone, cell
+// height 128 -> 1.174 ms, 256 -> 1.149, 336 -> 1.157, 352 -> 1.053, 368 -> 1.076, 384 -> 1.071, 400 -> 1.073, 416 -> 1.148,
+// 448 -> 1.102, 480 -> 1.125, 512 -> 1.145, 640 -> 1.051, 720 -> 1.067, one row of 32-px columns -> 1.090: tall beats short,
+// with +-4 % of scene-dependent scatter on top (a height derived from the L2 size, the depth and the template diagonal was
+// tried and landed on 480: the scatter is larger than what such a model resolves, so the height is a constant).
 constexpr int kSearchCellW = 128, kSearchCellH = 384;
 size_t search_order_temp_bytes(int64_t n_hyp);
 void launch_search_order(const TemplatesView& tv, const SceneView& sv, const SearchLaunch& sl, uint32_t* d_keys, uint32_t* d_keys_out,
