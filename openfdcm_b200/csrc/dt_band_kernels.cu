@@ -258,7 +258,7 @@ struct RowMeta {
 template <bool kFromG, bool kRev>
 __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restrict__ info_row, const uint16_t* __restrict__ g,
                                               const uint16_t* __restrict__ g_row, const MapDims& dm, int d, int row0, int x_begin,
-                                              int x_end, int lane, int rsel, const uint32_t* __restrict__ cand) {
+                                              int x_end, int lane, int rsel, const uint32_t* __restrict__ cand, int* claim = nullptr) {
     const int W = dm.W, Wm1 = dm.W - 1;
     const uint32_t mle = 0xFFFFFFFFu >> (31 - rsel), mge = 0xFFFFFFFFu << rsel;
     const int l31 = 31 - rsel;
@@ -270,6 +270,13 @@ __device__ __forceinline__ void envelope_half(RowStack& st, const uint2* __restr
     uint32_t cw_next = 0xFFFFFFFFu;
     if (cand && nchunks > 0) cw_next = cand[chunk_x0(0) >> 5];
     for (int c = 0; c < nchunks; ++c) {
+        if (claim) {
+            // the two warps of a band walk towards each other over the same range and claim their chunks one by one: they meet
+            // where their work (not their column count) is equal, and neither waits for the other at the join
+            int ok = 0;
+            if (lane == 0) ok = atomicAdd(claim, 1) < nchunks;
+            if (!__shfl_sync(0xffffffffu, ok, 0)) break;
+        }
         const int x0 = chunk_x0(c);
         const uint2 e = e_next;
         const uint32_t cw = cw_next;
@@ -391,6 +398,7 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
                                                          RowMeta* __restrict__ row_meta, int xsplit, int band_lo, int band_hi, int band_off) {
     extern __shared__ __align__(16) unsigned char band_smem[];
     __shared__ int s_kright[32];
+    __shared__ int s_claim;                                 // chunks of the 32-row pass handed out so far (both warps)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint2* ring_all = reinterpret_cast<uint2*>(band_smem);                                   // [2][kRing * 32]
     uint32_t* s_cand = reinterpret_cast<uint32_t*>(band_smem + band_alias_bytes(dm.pitch)); // [wwords]
@@ -413,6 +421,7 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
     uint2* row_entries = spill_all + prow * maxdepth;
 
     const uint32_t* cand = nullptr;
+    if (threadIdx.x == 0) s_claim = 0;                      // (the candidate phase below has two CTA barriers before its first use)
     if (!kFromG) {
         // ---- candidate phase ----
         // A band inside the rows that can hold edge pixels needs both passes: warp 0 takes the band's first row, warp 1 its
@@ -425,19 +434,34 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
         const int rsel = one_sided ? (b < band_lo ? min(31, dm.H - 1 - row0) : 0) : (warp == 0 ? 0 : min(31, dm.H - 1 - row0));
         const uint32_t mle = 0xFFFFFFFFu >> (31 - rsel), mge = 0xFFFFFFFFu << rsel;
         bool any = false;
-        for (int x0 = one_sided ? warp * 32 : 0; x0 < dm.pitch; x0 += one_sided ? 64 : 32) {
-            const uint2 e = x0 + lane < dm.W ? info_row[x0] : make_uint2(0u, 0xFFFFFFFFu);
-            uint32_t gv = 0xFFFFu;
-            if (e.x != 0u || e.y != 0xFFFFFFFFu) {
-                const uint32_t above = e.x & mle, below = e.x & mge;
-                const int up = rsel + (above ? __clz(above) - 31 : (int)(e.y & 0xFFFFu));
-                const int dn = (31 - rsel) + (below ? __ffs(below) - 1 - 31 : (int)(e.y >> 16));
-                gv = (uint32_t)min(up, dn);
-                any = true;
+        // (four record loads in flight per lane: the loop runs at the latency of its loads otherwise -- 12 % of the kernel's
+        // stall samples sat on the first use of `e`)
+        constexpr int kStageUnroll = 4;
+        const int xstep = one_sided ? 64 : 32;
+        for (int xb = one_sided ? warp * 32 : 0; xb < dm.pitch; xb += kStageUnroll * xstep) {
+            uint2 ev[kStageUnroll];
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int x0 = xb + u * xstep;
+                ev[u] = (x0 < dm.pitch && x0 + lane < dm.W) ? info_row[x0] : make_uint2(0u, 0xFFFFFFFFu);
             }
-            s_g[x0 + lane] = (uint16_t)gv;
-            const uint32_t inside = __ballot_sync(0xffffffffu, e.x != 0u);
-            if ((one_sided || warp == 0) && lane == 0) s_cand[x0 >> 5] = inside;   // columns with an edge pixel inside the band
+#pragma unroll
+            for (int u = 0; u < kStageUnroll; ++u) {
+                const int x0 = xb + u * xstep;
+                if (x0 >= dm.pitch) break;                 // (uniform)
+                const uint2 e = ev[u];
+                uint32_t gv = 0xFFFFu;
+                if (e.x != 0u || e.y != 0xFFFFFFFFu) {
+                    const uint32_t above = e.x & mle, below = e.x & mge;
+                    const int up = rsel + (above ? __clz(above) - 31 : (int)(e.y & 0xFFFFu));
+                    const int dn = (31 - rsel) + (below ? __ffs(below) - 1 - 31 : (int)(e.y >> 16));
+                    gv = (uint32_t)min(up, dn);
+                    any = true;
+                }
+                s_g[x0 + lane] = (uint16_t)gv;
+                const uint32_t inside = __ballot_sync(0xffffffffu, e.x != 0u);
+                if ((one_sided || warp == 0) && lane == 0) s_cand[x0 >> 5] = inside;   // columns with an edge pixel inside the band
+            }
         }
         __syncthreads();
         // lane = column segment; the segment length in 16-bit words is 2 (mod 4): consecutive lanes hit different banks
@@ -457,35 +481,19 @@ __global__ void __launch_bounds__(64) dt_row_band_kernel(const uint2* __restrict
         }
         __syncthreads();                                    // the mask is complete; the staging area becomes the ring
         cand = s_cand;
-        // split column of THIS band: the 32-column word at which half of its candidate columns have passed, so that the
-        // two warps (left stack ascending, right stack descending) get equal shares and neither waits at the join
-        {
-            int tot = 0;
-            for (int w = lane; w < dm.wwords; w += 32) tot += __popc(s_cand[w]);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-            int run = 0, split_w = dm.wwords;               // first word with (candidates before it) * 2 >= total
-            for (int w0 = 0; w0 < dm.wwords && split_w == dm.wwords; w0 += 32) {
-                const int c = w0 + lane < dm.wwords ? __popc(s_cand[w0 + lane]) : 0;
-                int inc = c;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-                const unsigned hit = __ballot_sync(0xffffffffu, 2 * (run + inc - c) >= tot);
-                if (hit) split_w = w0 + __ffs(hit) - 1;
-                run += __shfl_sync(0xffffffffu, inc, 31);
-            }
-            xsplit = min(dm.pitch, split_w * 32);
-        }
     }
 
+    // product path: no fixed split column, the warps claim 32-column chunks from their side until they meet (s_claim);
+    // explicit-g path (tests): the launcher's split column
+    int* claim = kFromG ? nullptr : &s_claim;
     RowStack st;
     if (warp == 1) {
         st.init(ring_addr, row_entries + (maxdepth - 1), -1);
-        envelope_half<kFromG, true>(st, info_row, g, g_row, dm, d, row0, xsplit, dm.pitch, lane, lane, cand);
+        envelope_half<kFromG, true>(st, info_row, g, g_row, dm, d, row0, kFromG ? xsplit : 0, dm.pitch, lane, lane, cand, claim);
         s_kright[lane] = st.park();
     } else {
         st.init(ring_addr, row_entries, 1);
-        envelope_half<kFromG, false>(st, info_row, g, g_row, dm, d, row0, 0, xsplit, lane, lane, cand);
+        envelope_half<kFromG, false>(st, info_row, g, g_row, dm, d, row0, 0, kFromG ? xsplit : dm.pitch, lane, lane, cand, claim);
     }
     __syncthreads();
     if (warp != 0) return;
