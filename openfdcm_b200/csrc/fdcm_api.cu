@@ -115,11 +115,26 @@ extern "C" fdcm_status fdcm_set_stream(int32_t device, void* cuda_stream) {
 }
 
 struct ProfEntry { double total_ms = 0; long long launches = 0; double bytes = 0; };
-struct ProfPending { std::string name; cudaEvent_t a, b; double bytes; };
+struct ProfPending { const char* name; cudaEvent_t a, b; double bytes; int device; };
 static bool g_prof_on = false;
 static std::vector<std::string> g_prof_order;
 static std::map<std::string, ProfEntry> g_prof;
 static std::vector<ProfPending> g_prof_pending;
+// timing events are recycled (per device): creating and destroying two events per kernel scope cost ~0.1 ms of driver calls
+// per profiled step, most of it after the step's host synchronisation
+static std::map<int, std::vector<cudaEvent_t>> g_prof_events;
+static cudaEvent_t prof_event_get(int device) {   // (g_mutex held)
+    auto& pool = g_prof_events[device];
+    cudaEvent_t e = nullptr;
+    if (!pool.empty()) {
+        e = pool.back();
+        pool.pop_back();
+    } else {
+        cudaEventCreate(&e);
+    }
+    return e;
+}
+static void prof_event_put(int device, cudaEvent_t e) { g_prof_events[device].push_back(e); }   // (g_mutex held)
 
 struct KernelScope {   // brackets one kernel launch
     cudaStream_t s;
@@ -128,10 +143,15 @@ struct KernelScope {   // brackets one kernel launch
     KernelScope(const char* name, double bytes, cudaStream_t stream, int n_kernels = 1) : s(stream), on(g_prof_on) {
         g_launches.fetch_add(n_kernels, std::memory_order_relaxed);
         if (on) {
-            p.name = name;
+            p.name = name;                                  // (string literals)
             p.bytes = bytes;
-            cudaEventCreate(&p.a);
-            cudaEventCreate(&p.b);
+            p.device = 0;
+            cudaGetDevice(&p.device);
+            {
+                std::lock_guard<std::mutex> lk(g_mutex);
+                p.a = prof_event_get(p.device);
+                p.b = prof_event_get(p.device);
+            }
             cudaEventRecord(p.a, s);
         }
     }
@@ -155,8 +175,8 @@ static void prof_resolve() {   // call after the stream has been synchronised
             e.launches += 1;
             e.bytes = p.bytes;
         }
-        cudaEventDestroy(p.a);
-        cudaEventDestroy(p.b);
+        prof_event_put(p.device, p.a);
+        prof_event_put(p.device, p.b);
     }
     g_prof_pending.clear();
 }
@@ -182,8 +202,8 @@ static void prof_resolve_finished() {
             e.launches += 1;
             e.bytes = p.bytes;
         }
-        cudaEventDestroy(p.a);
-        cudaEventDestroy(p.b);
+        prof_event_put(p.device, p.a);
+        prof_event_put(p.device, p.b);
     }
     g_prof_pending.swap(keep);
 }
