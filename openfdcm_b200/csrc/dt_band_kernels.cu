@@ -1171,11 +1171,8 @@ struct L1Config {
     static_assert(kFillWarps * 32 <= kThreads, "");
 };
 
-#ifndef FDCM_AB_L1_MINB
-#define FDCM_AB_L1_MINB 3
-#endif
 template <int D>
-__global__ void __launch_bounds__(L1Config<D>::kThreads, FDCM_AB_L1_MINB)
+__global__ void __launch_bounds__(L1Config<D>::kThreads, 3)
 dt_l1_propagate_kernel(const uint2* __restrict__ info, float* __restrict__ planes, MapDims dm, int nbands,
                        const __grid_constant__ PropParams pp) {
     using C = L1Config<D>;
