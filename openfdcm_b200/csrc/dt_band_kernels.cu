@@ -932,11 +932,13 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
     __shared__ int4 s_meta[D];                               // {k_left, entries, array offset of the right entries, first right pixel}
     __shared__ uint16_t s_pref[kFPMaxChunks][32];            // per chunk: units of the planes before plane d ([D]: all units)
     __shared__ uint8_t s_jl[kFPMaxChunks][32];               // per chunk: first batch of plane d that reaches into the chunk
+    __shared__ int s_next_unit;                              // units of the current chunk handed out so far
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int y = (int)blockIdx.x < na ? ya0 + (int)blockIdx.x : yb0 + ((int)blockIdx.x - na);   // rows [ya0, ya0 + na) then [yb0, ...)
     const int Hp = ((dm.H + 31) >> 5) << 5;                  // workspace rows per plane
     const int nchunks = (dm.W + C::kChunk - 1) / C::kChunk;
 
+    if (threadIdx.x == 0) s_next_unit = 0;
     // ---- first pixel of every batch (warp w: planes w and w + kWarps; the arrays hold resolved entries: dt_resolve_kernel) ----
 #pragma unroll
     for (int p = 0; p < C::kPlanesPerWarp; ++p) {
@@ -995,11 +997,18 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
                     rf.load_unit(spill_all + ((size_t)d * Hp + y) * maxdepth, m.x, m.y, m.z, j, (int)s_first[d][j + 1], lane);
                     return d;
                 };
+                // (units are claimed, not dealt: a warp that drew batches of one-pixel entries takes fewer of them, and the
+                // warps reach the barrier behind the fill together)
+                auto claim = [&]() {
+                    int u = 0;
+                    if (lane == 0) u = atomicAdd(&s_next_unit, 1);
+                    return __shfl_sync(0xffffffffu, u, 0);
+                };
                 RowFill cur, nxt;
-                int u = warp, d_cur = 0, d_nxt = 0;
+                int u = claim(), d_cur = 0, d_nxt = 0;
                 if (u < n_units) d_cur = load(u, cur);
                 while (u < n_units) {
-                    const int u2 = u + C::kWarps;
+                    const int u2 = claim();
                     if (u2 < n_units) d_nxt = load(u2, nxt);
                     cur.write_unit(q0, q0 + C::kChunk, fp_tile + (size_t)d_cur * C::kChunk, lane);
                     cur.be = nxt.be;
@@ -1019,6 +1028,7 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
             }
         }
         __syncthreads();
+        if (threadIdx.x == 0) s_next_unit = 0;               // (nobody claims between the two barriers)
         // ---- propagate: one pixel per thread ----
         propagate_from_tile<D>(fp_tile, C::kChunk, q0, y, planes, dm, pp, sqrt_first);
         __syncthreads();
