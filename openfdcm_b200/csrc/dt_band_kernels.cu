@@ -982,7 +982,7 @@ dt_fill_propagate_kernel(const uint2* __restrict__ spill_all /* resolved entries
 
     for (int ch = 0; ch < nchunks; ++ch) {
         const int q0 = ch * C::kChunk;
-        // ---- fill: the batches that reach into the chunk, dealt round-robin to the warps ----
+        // ---- fill: the batches that reach into the chunk, claimed one by one by the warps ----
         {
             const int pref = s_pref[ch][lane], jl = s_jl[ch][lane];     // lane = plane
             const int n_units = __shfl_sync(0xffffffffu, pref, D);
